@@ -1,0 +1,223 @@
+"""ctypes view of include/gab1pde.h and the loader for the CUDA library.
+
+The product path has exactly one implementation: libgab1pde.so (hand-written sm_100a kernels).
+If the library is missing or no CUDA device is usable the calls raise — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+ABI_VERSION = 1
+N_CO, N_D, N_K = 5, 7, 17
+N_MATRICES, N_VECTORS = 12, 11
+
+GEOM_SPHERICAL, GEOM_RECT = 0, 1
+SFK_DIFFUSIBLE, SFK_MEMBRANE, SFK_BOTH_FROZEN = 0, 1, 2
+BC_FOR_BREAK, BC_WHILE = 0, 1
+SAVE_T_GE_TSAVE, SAVE_MODULUS = 0, 1
+PG1TOT_VIA_STOT, PG1TOT_CHAIN = 0, 1
+OUT_FINAL4, OUT_FULL, OUT_SIX, OUT_PCT_BOUND, OUT_FINAL_STATE = 0, 1, 2, 3, 4
+ARITH_FAST, ARITH_STRICT = 0, 1
+
+ST_NAN, ST_ITER_CAP, ST_SHORT, ST_OVERFLOW, ST_THROW = 1, 2, 4, 8, 16
+
+MATRIX_NAMES = ("iSFK", "aSFK", "GRB2", "GAB1", "SHP2", "G2G1", "G2PG1", "G2PG1S", "PG1", "PG1S", "PG1tot", "PG1Stot")
+VECTOR_NAMES = ("pE", "mE", "mES", "mESmES", "E", "EG2", "EG2G1", "EG2PG1", "EG2PG1S", "EGFR_SHP2", "t_out")
+MASK_ALL = 0xFFF
+MASK_FITTING = (1 << 1) | (1 << 9) | (1 << 7)
+
+
+class Opts(C.Structure):
+    """struct gab1_opts (include/gab1pde.h)."""
+
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("geometry", C.c_int32),
+        ("sfk_mode", C.c_int32),
+        ("bc_loop", C.c_int32),
+        ("save_rule", C.c_int32),
+        ("pg1tot_form", C.c_int32),
+        ("out_mode", C.c_int32),
+        ("matrix_mask", C.c_uint32),
+        ("maxiters", C.c_int32),
+        ("Nr", C.c_int32),
+        ("Nts", C.c_int32),
+        ("arith", C.c_int32),
+        ("tol", C.c_double),
+        ("R", C.c_double),
+        ("dr", C.c_double),
+        ("tf", C.c_double),
+        ("dt_save", C.c_double),
+        ("t_prechase", C.c_double),
+        ("pct_mul", C.c_double),
+        ("pct_div", C.c_double),
+        ("n_devices", C.c_int32),
+        ("reserved", C.c_int32),
+        ("device_ids", C.POINTER(C.c_int32)),
+    ]
+
+
+def make_opts(*, R=10.0, dr=0.1, tf=5.0, Nts=100, Nr=None, dt_save=None, maxiters=100, tol=1e-6,
+              geometry=GEOM_SPHERICAL, sfk_mode=SFK_DIFFUSIBLE, bc_loop=BC_FOR_BREAK,
+              save_rule=SAVE_T_GE_TSAVE, pg1tot_form=PG1TOT_VIA_STOT, out_mode=OUT_FULL,
+              matrix_mask=MASK_ALL, arith=ARITH_FAST, t_prechase=-1.0, pct_mul=1.0, pct_div=1.0,
+              n_devices=1) -> Opts:
+    o = Opts()
+    o.abi_version = ABI_VERSION
+    o.geometry, o.sfk_mode, o.bc_loop = geometry, sfk_mode, bc_loop
+    o.save_rule, o.pg1tot_form, o.out_mode = save_rule, pg1tot_form, out_mode
+    o.matrix_mask = matrix_mask
+    o.maxiters = int(maxiters)
+    o.Nr = int(np.ceil(R / dr)) if Nr is None else int(Nr)   # Nr = Int64(ceil(R/dr)), basepdesolver.jl:71
+    o.Nts = int(Nts)
+    o.arith = arith
+    o.tol = float(tol)
+    o.R, o.dr, o.tf = float(R), float(dr), float(tf)
+    o.dt_save = float(tf) / int(Nts) if dt_save is None else float(dt_save)  # dt_save = tf/Nts, basepdesolver.jl:31
+    o.t_prechase = float(t_prechase)
+    o.pct_mul, o.pct_div = float(pct_mul), float(pct_div)
+    o.n_devices = int(n_devices)
+    o.reserved = 0
+    o.device_ids = None
+    return o
+
+
+def out_doubles_per_set(o: Opts) -> int:
+    P, Cn = o.Nr + 1, o.Nts + 1
+    nm = bin(o.matrix_mask & MASK_ALL).count("1")
+    return {OUT_FINAL4: 4 * P, OUT_FULL: nm * P * Cn + N_VECTORS * Cn, OUT_SIX: 6, OUT_PCT_BOUND: 1,
+            OUT_FINAL_STATE: 10 * P + 8}[o.out_mode]
+
+
+def full_matrix_offset(o: Opts, m: int) -> int:
+    if not (o.matrix_mask >> m) & 1:
+        return -1
+    return bin(o.matrix_mask & ((1 << m) - 1)).count("1") * (o.Nr + 1) * (o.Nts + 1)
+
+
+def full_vector_offset(o: Opts, v: int) -> int:
+    return bin(o.matrix_mask & MASK_ALL).count("1") * (o.Nr + 1) * (o.Nts + 1) + v * (o.Nts + 1)
+
+
+_dp = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+
+SOLVE_ARGTYPES = [C.POINTER(Opts), C.c_int64, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp, _i32p, _i32p, _i64p, _i64p]
+
+
+def _ptr(a, typ):
+    return None if a is None else a.ctypes.data_as(typ)
+
+
+def call_solve(fn, o: Opts, Co, D, k, dt, r, *extra):
+    """Marshal numpy arrays into a gab1_solve_batch-shaped function and return its outputs."""
+    D = np.ascontiguousarray(D, dtype=np.float64).reshape(-1, N_D)
+    k = np.ascontiguousarray(k, dtype=np.float64).reshape(-1, N_K)
+    S = D.shape[0]
+    if k.shape[0] != S:
+        raise ValueError("D and k must hold the same number of parameter sets")
+    Co = np.ascontiguousarray(Co, dtype=np.float64)
+    if Co.ndim == 1:
+        if Co.shape[0] != N_CO:
+            raise ValueError("Co must have 5 entries")
+        co_stride = 0
+    else:
+        if Co.shape != (S, N_CO):
+            raise ValueError("Co must be (5,) or (S, 5)")
+        co_stride = N_CO
+    dt = np.ascontiguousarray(np.broadcast_to(np.asarray(dt, dtype=np.float64), (S,)))
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    if r.shape != (o.Nr + 1,):
+        # the reference indexes r[Nr+1] (basepdesolver.jl:151,206); a shorter grid is a BoundsError there
+        raise IndexError(f"r has {r.shape[0]} nodes but Nr+1 = {o.Nr + 1}")
+    n = out_doubles_per_set(o)
+    out = np.zeros((S, n), dtype=np.float64)
+    status = np.zeros(S, dtype=np.int32)
+    n_saved = np.zeros(S, dtype=np.int32)
+    n_steps = np.zeros(S, dtype=np.int64)
+    n_bc = np.zeros(S, dtype=np.int64)
+    rc = fn(C.byref(o), S, _ptr(Co, _dp), co_stride, _ptr(D, _dp), _ptr(k, _dp), _ptr(dt, _dp), _ptr(r, _dp),
+            _ptr(out, _dp), _ptr(status, _i32p), _ptr(n_saved, _i32p), _ptr(n_steps, _i64p), _ptr(n_bc, _i64p), *extra)
+    return rc, out, status, n_saved, n_steps, n_bc
+
+
+class Gab1Error(RuntimeError):
+    pass
+
+
+_LIB = None
+LIB_NAME = "libgab1pde.so"
+
+
+def lib_path() -> Path:
+    return Path(__file__).resolve().parent / LIB_NAME
+
+
+def load_library():
+    """dlopen libgab1pde.so (built in-tree by __graft_entry__.build()); raises if it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = Path(os.environ.get("GAB1PDE_LIB", lib_path()))
+    if not p.exists():
+        raise Gab1Error(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                        "There is no CPU fallback.")
+    lib = C.CDLL(str(p))
+    lib.gab1_solve_batch.argtypes = SOLVE_ARGTYPES
+    lib.gab1_solve_batch.restype = C.c_int
+    lib.gab1_solve_batch_device.argtypes = [C.POINTER(Opts), C.c_int32, C.c_void_p, C.c_int64,
+                                            C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gab1_solve_batch_device.restype = C.c_int
+    lib.gab1_workspace_bytes.argtypes = [C.c_int64]
+    lib.gab1_workspace_bytes.restype = C.c_size_t
+    lib.gab1_out_doubles_per_set.argtypes = [C.POINTER(Opts)]
+    lib.gab1_out_doubles_per_set.restype = C.c_int64
+    lib.gab1_full_matrix_offset.argtypes = [C.POINTER(Opts), C.c_int32]
+    lib.gab1_full_matrix_offset.restype = C.c_int64
+    lib.gab1_full_vector_offset.argtypes = [C.POINTER(Opts), C.c_int32]
+    lib.gab1_full_vector_offset.restype = C.c_int64
+    lib.gab1_opts_init.argtypes = [C.POINTER(Opts), C.c_double, C.c_double, C.c_double, C.c_int32]
+    lib.gab1_opts_init.restype = None
+    lib.gab1_default_dt.argtypes = [C.c_int64, _dp, _dp, C.c_double, _dp]
+    lib.gab1_default_dt.restype = C.c_int
+    lib.gab1_host_alloc.argtypes = [C.c_size_t]
+    lib.gab1_host_alloc.restype = C.c_void_p
+    lib.gab1_host_free.argtypes = [C.c_void_p]
+    lib.gab1_host_free.restype = None
+    lib.gab1_measure_fp64_tflops.argtypes = [C.c_int32, C.c_double]
+    lib.gab1_measure_fp64_tflops.restype = C.c_double
+    lib.gab1_kernel_launches.argtypes = []
+    lib.gab1_kernel_launches.restype = C.c_int64
+    lib.gab1_device_count.argtypes = []
+    lib.gab1_device_count.restype = C.c_int
+    lib.gab1_version.argtypes = []
+    lib.gab1_version.restype = C.c_int
+    lib.gab1_last_error.argtypes = []
+    lib.gab1_last_error.restype = C.c_char_p
+    _LIB = lib
+    return lib
+
+
+class CudaBackend:
+    """The product backend: every solve goes through gab1_solve_batch in libgab1pde.so."""
+
+    name = "cuda"
+
+    def __init__(self, n_devices: int = 1, arith: int = ARITH_FAST):
+        self.n_devices = n_devices
+        self.arith = arith
+
+    def solve(self, o: Opts, Co, D, k, dt, r):
+        lib = load_library()
+        o.n_devices = self.n_devices
+        o.arith = self.arith
+        rc, out, status, n_saved, n_steps, n_bc = call_solve(lib.gab1_solve_batch, o, Co, D, k, dt, r)
+        if rc != 0:
+            raise Gab1Error(f"gab1_solve_batch failed ({rc}): {lib.gab1_last_error().decode(errors='replace')}")
+        return out, status, n_saved, n_steps, n_bc

@@ -1,0 +1,89 @@
+"""Pins for the oracle that do not depend on another restatement (SURVEY.md §8c pins 1-3, 5)."""
+import numpy as np
+
+
+def test_discrete_invariants(pkg, ofe, ensemble):
+    """EGFR conservation holds step by step (terms cancel pairwise in basepdesolver.jl:220-231) and
+    iSFK + aSFK = CoSFK at every node when both share one diffusivity (MATLAB/finitediff_steady_state_BVP_comparison.m:81)."""
+    Co = pkg.params.base_Co()
+    res = ofe.pdesolver_batch(Co, ensemble[:4, :7], ensemble[:4, 7:], dr=0.4, tf=2.0, Nts=20, tol=1e-4, maxiters=20)
+    v = {n: res.vector(n) for n in pkg.abi.VECTOR_NAMES}
+    tot = v["mE"] + v["mES"] + 2 * (v["mESmES"] + v["E"] + v["EG2"] + v["EG2G1"] + v["EG2PG1"] + v["EG2PG1S"])
+    assert np.abs(tot / Co[4] - 1).max() < 1e-12
+    sfk = res.matrix("iSFK") + res.matrix("aSFK")
+    assert np.abs(sfk / Co[0] - 1).max() < 1e-12
+    # derived outputs
+    np.testing.assert_array_equal(res.matrix("PG1Stot"), res.matrix("PG1S") + res.matrix("G2PG1S"))
+    np.testing.assert_array_equal(v["pE"][:, 1:], (2.0 * (v["E"] + v["EG2"] + v["EG2G1"] + v["EG2PG1"] + v["EG2PG1S"]) * 100.0 / Co[4])[:, 1:])
+    # column 1 is the initial state, t_out increases by ~dt_save
+    assert np.all(res.matrix("iSFK")[:, :, 0] == Co[0]) and np.all(res.matrix("aSFK")[:, :, 0] == 0)
+    assert np.allclose(np.diff(v["t_out"], axis=1), 0.1, atol=2e-3)
+
+
+def test_steady_asfk_profile_matches_closed_form(pkg, ofe):
+    """At t = 5 min the aSFK profile is close to the steady solution C(r) = C(R) * (R/r) * sinh(m r)/sinh(m R),
+    m = sqrt(kSi/D_S)  (MATLAB/finitediff_steady_state_BVP_comparison.m:98-104)."""
+    Co = pkg.params.base_Co()
+    D, k = pkg.params.DIFFS_BASE, pkg.params.KVALS_BASE
+    sol, r = ofe.sapdesolver(Co, D, k, dr=0.2, tf=5.0)
+    m = np.sqrt(k[9] / D[0])
+    rr = r[1:]
+    shape = (10.0 / rr) * np.sinh(m * rr) / np.sinh(m * 10.0)
+    assert np.abs(sol.aSFK[1:] / sol.aSFK[-1] / shape - 1).max() < 0.02
+
+
+def test_pct_shp2_bound_gab1_near_fitting_target(pkg, ofe, ensemble):
+    """Posterior-median parameters give % SHP2-bound GAB1 inside the experimental 26.4 +/- 9.4
+    (exptl_pct_SHP2-bound-GAB1.csv; SURVEY.md §4 probe: rows 0,1 -> 23.46 %, 26.05 % at dr = 0.2)."""
+    Co = pkg.params.base_Co()
+    pct, _ = ofe.pct_shp2_bound_gab1(Co, ensemble[:2, :7], ensemble[:2, 7:])
+    assert abs(pct[0] - 23.46) < 0.01 and abs(pct[1] - 26.05) < 0.01
+    pct0, _ = ofe.pct_shp2_bound_gab1(Co, pkg.params.DIFFS_BASE[None], pkg.params.KVALS_BASE[None])
+    assert 17.0 < pct0[0] < 36.0
+
+
+def test_pct_equals_epilogue_of_full_solution(pkg, ofe, ensemble):
+    Co = pkg.params.base_Co()
+    volCF, surfCF = pkg.params.conversion_factors()
+    D, k = ensemble[5:7, :7], ensemble[5:7, 7:]
+    pct, _ = ofe.pct_shp2_bound_gab1(Co, D, k, dr=0.4, tf=1.0, Nts=10)
+    full = ofe.pdesolver_batch(Co, D, k, dr=0.4, tf=1.0, Nts=10, tol=1e-4, maxiters=20)
+    r = full.r
+    for i in range(2):
+        y = (full.matrix("PG1S")[i][:, -1] + full.matrix("G2PG1S")[i][:, -1]) * (r * r)
+        acc = 0.0
+        for j in range(len(r) - 1):
+            acc += (r[j + 1] - r[j]) * (y[j] + y[j + 1])
+        ave = 0.5 * acc * 3.0 / (10.0 * 10.0 * 10.0)
+        tot = ave + full.vector("EG2PG1S")[i][-1] * volCF / surfCF
+        assert pct[i] == tot / Co[2] * 100.0
+
+
+def test_known_diverging_row_and_nan_count(pkg, ofe, ensemble):
+    """Row 76 (kG1p = 71.3) diverges at dr = 0.2 but not at dr = 0.1; the NaN filter of
+    run_ensemble (get_param_posteriors.jl:155) drops it."""
+    Co = pkg.params.base_Co()
+    rows = ofe.run_ensemble("pdesolver", ensemble[74:77], Co, Nts=10)       # 0-based rows 74, 75, 76
+    assert [x.index for x in rows] == [1, 3]
+    sol = ofe.pdesolver(Co, ensemble[75, :7], ensemble[75, 7:], dr=0.1, Nts=4, tol=1e-4, maxiters=20)[0]
+    assert np.isfinite(sol.PG1S).all()
+
+
+def test_oracle_kat(pkg, ofe, ensemble):
+    """Known-answer vectors written by tests/golden/make_fixtures.py: guards the oracle's arithmetic against drift."""
+    from pathlib import Path
+    kat = np.load(Path(__file__).parent / "golden" / "oracle_kat.npz")
+    sub = ensemble[kat["rows"]]
+    Co = pkg.params.base_Co()
+    res = ofe.pdesolver_batch(Co, sub[:, :7], sub[:, 7:], dr=0.4, tf=1.0, Nts=10, tol=1e-4, maxiters=20)
+    np.testing.assert_array_equal(res.out, kat["full_dr04_tf1"])
+    np.testing.assert_array_equal(res.n_bc_iters, kat["full_dr04_tf1_nbc"])
+    res = ofe.sapdesolver_batch(Co, sub[:, :7], sub[:, 7:], dr=0.2, tf=0.5)
+    np.testing.assert_array_equal(res.out, kat["final4_dr02_tf05"])
+    res = ofe.sapdesolver_batch(pkg.params.hela_Co(), sub[:, :7], sub[:, 7:], dr=0.2, tf=0.5, membSFK=True)
+    np.testing.assert_array_equal(res.out, kat["final4_memb_dr02_tf05"])
+    res = ofe.sapdesolver_batch(Co, sub[:, :7], sub[:, 7:], dr=0.2, tf=0.5, out_mode=pkg.abi.OUT_SIX)
+    np.testing.assert_array_equal(res.out, kat["six_dr02_tf05"])
+    res = ofe.pdesolver_batch(Co, sub[:, :7], sub[:, 7:], dr=0.25, tf=0.5, Nts=5, tol=1e-4, maxiters=20,
+                              geometry=pkg.abi.GEOM_RECT, pg1tot_form=pkg.abi.PG1TOT_CHAIN)
+    np.testing.assert_array_equal(res.out, kat["full_rect_dr025_tf05"])
