@@ -1,0 +1,432 @@
+// gab1pde.cu — C ABI of libgab1pde.so (include/gab1pde.h): option checking, work ordering, kernel launch,
+// multi-GPU sharding of the host entry point.  No CPU implementation of the solver lives here.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cub/device/device_radix_sort.cuh>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "gab1pde.h"
+#include "solver_kernel.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e_ = (expr);                                                                             \
+    if (e_ != cudaSuccess) return fail(-100 - (int)e_, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+int popcount12(uint32_t m) { return __builtin_popcount(m & GAB1_MASK_ALL_MATRICES); }
+
+int check_opts(const gab1_opts* o) {
+  if (!o) return fail(-1, "opts is NULL");
+  if (o->abi_version != GAB1_ABI_VERSION) return fail(-1, "abi_version %d != %d", o->abi_version, GAB1_ABI_VERSION);
+  if (o->Nr < 2) return fail(-2, "Nr must be >= 2");
+  if (o->Nts < 1) return fail(-2, "Nts must be >= 1");
+  if (o->maxiters < 0) return fail(-2, "maxiters must be >= 0");
+  if (o->geometry < 0 || o->geometry > 1 || o->sfk_mode < 0 || o->sfk_mode > 2 || o->bc_loop < 0 || o->bc_loop > 1 ||
+      o->save_rule < 0 || o->save_rule > 1 || o->pg1tot_form < 0 || o->pg1tot_form > 1 || o->out_mode < 0 ||
+      o->out_mode > 4 || o->arith < 0 || o->arith > 1)
+    return fail(-3, "an enum field of gab1_opts is out of range");
+  if (!(o->dr > 0.0) || !(o->R > 0.0)) return fail(-2, "R and dr must be positive");
+  return 0;
+}
+
+// nodes per lane for a one-warp-per-set launch: nodes 1..Nr over 32 lanes
+int pick_K(int Nr) {
+  for (int K : {1, 2, 4, 8})
+    if (Nr <= 32 * K) return K;
+  return 0;
+}
+
+// ---- descending-work ordering: key = number of time steps, largest first -------------------------------------
+__global__ void work_keys_kernel(long long S, const double* dt, double tf, unsigned* keys, int* vals) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= S) return;
+  const double n = ceil(tf / dt[i]);
+  keys[i] = (n >= 0.0 && n < 4.0e9) ? (unsigned)n : 0u;   // unusable dt: no work, goes last
+  vals[i] = (int)i;
+}
+
+struct Workspace {   // carved out of the caller's workspace buffer
+  unsigned* counter;
+  unsigned *keys_in, *keys_out;
+  int *vals_in, *vals_out;
+  void* cub_tmp;
+  size_t cub_bytes;
+};
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+size_t cub_bytes_for(long long S) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const unsigned*)nullptr, (unsigned*)nullptr,
+                                            (const int*)nullptr, (int*)nullptr, (int)S);
+  return bytes;
+}
+
+size_t carve(Workspace& w, void* base, long long S) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* p = base ? (char*)base + off : nullptr; off += align_up(bytes, 256); return p; };
+  w.counter = (unsigned*)take(256);
+  w.keys_in = (unsigned*)take(sizeof(unsigned) * (size_t)S);
+  w.keys_out = (unsigned*)take(sizeof(unsigned) * (size_t)S);
+  w.vals_in = (int*)take(sizeof(int) * (size_t)S);
+  w.vals_out = (int*)take(sizeof(int) * (size_t)S);
+  w.cub_bytes = cub_bytes_for(S);
+  w.cub_tmp = take(w.cub_bytes);
+  return off;
+}
+
+template <int K, bool STRICT>
+int launch(const gab1::KernelArgs& args, int device, cudaStream_t stream) {
+  static std::mutex mu;
+  static int blocks_per_sm[64] = {0};
+  static int sms[64] = {0};
+  const size_t smem = (size_t)4 * (gab1::WS_HDR + 2 * (size_t)args.P_pad) * sizeof(double);
+  auto kern = gab1::solve_kernel<K, STRICT>;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 64 && blocks_per_sm[device] == 0) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      int n = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 128, smem));
+      if (n < 1) return fail(-5, "kernel does not fit on an SM (K=%d, smem=%zu)", K, smem);
+      blocks_per_sm[device] = n;
+      CUDA_TRY(cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device));
+    }
+  }
+  int nb = 0, nsm = 0;
+  if (device < 64) { nb = blocks_per_sm[device]; nsm = sms[device]; }
+  if (nb == 0) {
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 128, smem));
+    CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+  }
+  // persistent grid: a multiple of the SM count; never more warps than sets
+  long long grid = (long long)nsm * nb;
+  const long long need = (args.S + 3) / 4;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, 128, smem, stream>>>(args);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long S, const double* Co, long long Co_stride,
+                 const double* D, const double* k, const double* dt, const double* r, double* out, int* status,
+                 int* n_saved, long long* n_steps, long long* n_bc, void* workspace) {
+  if (int rc = check_opts(o)) return rc;
+  if (S < 0) return fail(-2, "S must be >= 0");
+  if (S == 0) return 0;
+  if (S > 2000000000LL) return fail(-2, "S too large for one call");
+  if (Co_stride != 0 && Co_stride != GAB1_N_CO) return fail(-2, "Co_stride must be 0 or 5");
+  if (!Co || !D || !k || !dt || !r || !out || !workspace) return fail(-2, "a required buffer is NULL");
+  const int K = pick_K(o->Nr);
+  if (K == 0) return fail(-6, "Nr = %d: grids with more than 256 nodes are not supported by this build", o->Nr);
+  CUDA_TRY(cudaSetDevice(device));
+
+  Workspace w;
+  carve(w, workspace, S);
+  gab1::KernelArgs a;
+  memset(&a, 0, sizeof a);
+  a.o = *o;
+  a.o.device_ids = nullptr;
+  a.S = S;
+  a.Co = Co; a.Co_stride = Co_stride; a.D = D; a.k = k; a.dt = dt; a.r = r;
+  a.out = out; a.out_stride = gab1_out_doubles_per_set(o);
+  a.status = status; a.n_saved = n_saved; a.n_steps = n_steps; a.n_bc = n_bc;
+  a.order = w.vals_out;
+  a.counter = w.counter;
+  a.R_pow3 = pow(o->R, 3.0);
+  a.P_pad = (o->Nr + 1 + 3) & ~3;
+
+  CUDA_TRY(cudaMemsetAsync(w.counter, 0, sizeof(unsigned), stream));
+  CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)a.out_stride * (size_t)S, stream));
+  {
+    const int tb = 256;
+    work_keys_kernel<<<(unsigned)((S + tb - 1) / tb), tb, 0, stream>>>(S, dt, o->tf, w.keys_in, w.vals_in);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    size_t bytes = w.cub_bytes;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp, bytes, w.keys_in, w.keys_out, w.vals_in, w.vals_out,
+                                                       (int)S, 0, 32, stream));
+  }
+  const bool strict = o->arith == 1;
+  switch (K) {
+    case 1: return strict ? launch<1, true>(a, device, stream) : launch<1, false>(a, device, stream);
+    case 2: return strict ? launch<2, true>(a, device, stream) : launch<2, false>(a, device, stream);
+    case 4: return strict ? launch<4, true>(a, device, stream) : launch<4, false>(a, device, stream);
+    case 8: return strict ? launch<8, true>(a, device, stream) : launch<8, false>(a, device, stream);
+  }
+  return fail(-6, "no kernel for K=%d", K);
+}
+
+// ---- FP64 peak: register-resident DFMA chains ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* sink, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 123.456) sink[0] = s;
+}
+
+}  // namespace
+
+extern "C" {
+
+void gab1_opts_init(gab1_opts* o, double R, double dr, double tf, int32_t Nts) {
+  memset(o, 0, sizeof *o);
+  o->abi_version = GAB1_ABI_VERSION;
+  o->geometry = GAB1_GEOM_SPHERICAL;
+  o->sfk_mode = GAB1_SFK_DIFFUSIBLE;
+  o->bc_loop = GAB1_BC_FOR_BREAK;
+  o->save_rule = GAB1_SAVE_T_GE_TSAVE;
+  o->pg1tot_form = GAB1_PG1TOT_VIA_STOT;
+  o->out_mode = GAB1_OUT_FULL;
+  o->matrix_mask = GAB1_MASK_ALL_MATRICES;
+  o->maxiters = 100;                       // basepdesolver.jl:32
+  o->tol = 1.0e-6;                         // basepdesolver.jl:33
+  o->R = R; o->dr = dr; o->tf = tf;
+  o->Nr = (int32_t)ceil(R / dr);           // basepdesolver.jl:71
+  o->Nts = Nts;
+  o->dt_save = tf / Nts;                   // basepdesolver.jl:31
+  o->t_prechase = -1.0;
+  o->pct_mul = 1.0; o->pct_div = 1.0;
+  o->n_devices = 1;
+}
+
+int64_t gab1_out_doubles_per_set(const gab1_opts* o) {
+  if (!o) return 0;
+  const int64_t P = (int64_t)o->Nr + 1, C = (int64_t)o->Nts + 1;
+  switch (o->out_mode) {
+    case GAB1_OUT_FINAL4: return 4 * P;
+    case GAB1_OUT_FULL: return (int64_t)popcount12(o->matrix_mask) * P * C + GAB1_N_VECTORS * C;
+    case GAB1_OUT_SIX: return 6;
+    case GAB1_OUT_PCT_BOUND: return 1;
+    case GAB1_OUT_FINAL_STATE: return 10 * P + 8;
+  }
+  return 0;
+}
+
+int64_t gab1_full_matrix_offset(const gab1_opts* o, int32_t m) {
+  if (!o || m < 0 || m >= GAB1_N_MATRICES || !((o->matrix_mask >> m) & 1u)) return -1;
+  const int64_t P = (int64_t)o->Nr + 1, C = (int64_t)o->Nts + 1;
+  return (int64_t)popcount12(o->matrix_mask & ((1u << m) - 1u)) * P * C;
+}
+
+int64_t gab1_full_vector_offset(const gab1_opts* o, int32_t v) {
+  if (!o || v < 0 || v >= GAB1_N_VECTORS) return -1;
+  const int64_t P = (int64_t)o->Nr + 1, C = (int64_t)o->Nts + 1;
+  return (int64_t)popcount12(o->matrix_mask) * P * C + (int64_t)v * C;
+}
+
+int gab1_default_dt(int64_t S, const double* D, const double* k, double dr, double* dt) {
+  if (!D || !k || !dt) return fail(-2, "a required buffer is NULL");
+  for (int64_t i = 0; i < S; ++i) {
+    double mx = D[i * GAB1_N_D];
+    for (int q = 1; q < GAB1_N_D; ++q) mx = D[i * GAB1_N_D + q] > mx ? D[i * GAB1_N_D + q] : mx;
+    double sk = 0.0;
+    for (int q = 0; q < GAB1_N_K; ++q) sk += k[i * GAB1_N_K + q];
+    dt[i] = 1.0 / (2.0 * (mx / (dr * dr) + sk / 4)) * 0.99;
+  }
+  return 0;
+}
+
+size_t gab1_workspace_bytes(int64_t S) {
+  Workspace w;
+  return carve(w, nullptr, S < 1 ? 1 : S);
+}
+
+int gab1_solve_batch_device(const gab1_opts* o, int32_t device, void* stream, int64_t S, const double* Co,
+                            int64_t Co_stride, const double* D, const double* k, const double* dt, const double* r,
+                            double* out, int32_t* status, int32_t* n_saved, int64_t* n_steps, int64_t* n_bc_iters,
+                            void* workspace) {
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64_t must be long long");
+  return solve_device(o, device, (cudaStream_t)stream, S, Co, Co_stride, D, k, dt, r, out, status, n_saved,
+                      (long long*)n_steps, (long long*)n_bc_iters, workspace);
+}
+
+// One shard of the host entry point: copy in, solve, copy out, on its own stream.
+static int run_shard(const gab1_opts* o, int device, int64_t lo, int64_t hi, const double* Co, int64_t Co_stride,
+                     const double* D, const double* k, const double* dt, const double* r, double* out, int32_t* status,
+                     int32_t* n_saved, int64_t* n_steps, int64_t* n_bc) {
+  const int64_t S = hi - lo;
+  if (S <= 0) return 0;
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st;
+  CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  const int64_t nout = gab1_out_doubles_per_set(o);
+  const size_t P = (size_t)o->Nr + 1;
+  double *dCo = nullptr, *dD = nullptr, *dk = nullptr, *ddt = nullptr, *dr_ = nullptr, *dout = nullptr;
+  int32_t *dstatus = nullptr, *dsaved = nullptr;
+  int64_t *dsteps = nullptr, *dbc = nullptr;
+  void* ws = nullptr;
+  int rc = 0;
+  auto body = [&]() -> int {
+    const size_t nCo = Co_stride ? (size_t)S * GAB1_N_CO : GAB1_N_CO;
+    CUDA_TRY(cudaMalloc(&dCo, nCo * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&dD, (size_t)S * GAB1_N_D * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&dk, (size_t)S * GAB1_N_K * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&ddt, (size_t)S * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&dr_, P * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&dout, (size_t)S * nout * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&dstatus, (size_t)S * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&dsaved, (size_t)S * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&dsteps, (size_t)S * sizeof(int64_t)));
+    CUDA_TRY(cudaMalloc(&dbc, (size_t)S * sizeof(int64_t)));
+    CUDA_TRY(cudaMalloc(&ws, gab1_workspace_bytes(S)));
+    CUDA_TRY(cudaMemcpyAsync(dCo, Co + (Co_stride ? lo * Co_stride : 0), nCo * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dD, D + lo * GAB1_N_D, (size_t)S * GAB1_N_D * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dk, k + lo * GAB1_N_K, (size_t)S * GAB1_N_K * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ddt, dt + lo, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dr_, r, P * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (int e = solve_device(o, device, st, S, dCo, Co_stride, dD, dk, ddt, dr_, dout, dstatus, dsaved,
+                             (long long*)dsteps, (long long*)dbc, ws))
+      return e;
+    CUDA_TRY(cudaMemcpyAsync(out + lo * nout, dout, (size_t)S * nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status + lo, dstatus, (size_t)S * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (n_saved) CUDA_TRY(cudaMemcpyAsync(n_saved + lo, dsaved, (size_t)S * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (n_steps) CUDA_TRY(cudaMemcpyAsync(n_steps + lo, dsteps, (size_t)S * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (n_bc) CUDA_TRY(cudaMemcpyAsync(n_bc + lo, dbc, (size_t)S * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+  };
+  rc = body();
+  cudaFree(dCo); cudaFree(dD); cudaFree(dk); cudaFree(ddt); cudaFree(dr_); cudaFree(dout);
+  cudaFree(dstatus); cudaFree(dsaved); cudaFree(dsteps); cudaFree(dbc); cudaFree(ws);
+  cudaStreamDestroy(st);
+  return rc;
+}
+
+int gab1_solve_batch(const gab1_opts* o, int64_t S, const double* Co, int64_t Co_stride, const double* D, const double* k,
+                     const double* dt, const double* r, double* out, int32_t* status, int32_t* n_saved, int64_t* n_steps,
+                     int64_t* n_bc_iters) {
+  if (int rc = check_opts(o)) return rc;
+  if (S < 0) return fail(-2, "S must be >= 0");
+  if (S == 0) return 0;
+  if (!Co || !D || !k || !dt || !r || !out) return fail(-2, "a required buffer is NULL");
+  int visible = 0;
+  if (cudaGetDeviceCount(&visible) != cudaSuccess || visible < 1)
+    return fail(-7, "no CUDA device is visible; this library has no CPU fallback");
+  int nd = o->n_devices <= 0 ? visible : o->n_devices;
+  if (nd > visible && !o->device_ids) return fail(-7, "n_devices = %d but only %d CUDA devices are visible", nd, visible);
+  if (nd > S) nd = (int)S;
+  std::vector<int> devs(nd);
+  for (int i = 0; i < nd; ++i) devs[i] = o->device_ids ? o->device_ids[i] : i;
+
+  // contiguous shards with equal total step count, so that the gather is one copy per device
+  std::vector<int64_t> bounds(nd + 1, 0);
+  {
+    std::vector<double> work((size_t)S);
+    double total = 0.0;
+    for (int64_t i = 0; i < S; ++i) {
+      const double n = ceil(o->tf / dt[i]);
+      work[i] = (n > 0.0 && n < 4.0e9) ? n : 1.0;
+      total += work[i];
+    }
+    double acc = 0.0;
+    int g = 1;
+    for (int64_t i = 0; i < S && g < nd; ++i) {
+      acc += work[i];
+      if (acc >= total * g / nd) bounds[g++] = i + 1;
+    }
+    for (; g < nd; ++g) bounds[g] = S;
+    bounds[nd] = S;
+  }
+  if (nd == 1) return run_shard(o, devs[0], 0, S, Co, Co_stride, D, k, dt, r, out, status, n_saved, n_steps, n_bc_iters);
+
+  std::vector<int> rcs(nd, 0);
+  std::vector<std::string> msgs(nd);
+  std::vector<std::thread> th;
+  for (int g = 0; g < nd; ++g)
+    th.emplace_back([&, g]() {
+      rcs[g] = run_shard(o, devs[g], bounds[g], bounds[g + 1], Co, Co_stride, D, k, dt, r, out, status, n_saved, n_steps,
+                         n_bc_iters);
+      if (rcs[g]) msgs[g] = g_err;
+    });
+  for (auto& t : th) t.join();
+  for (int g = 0; g < nd; ++g)
+    if (rcs[g]) return fail(rcs[g], "device %d: %s", devs[g], msgs[g].c_str());
+  return 0;
+}
+
+void* gab1_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    fail(-8, "cudaHostAlloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+void gab1_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+double gab1_measure_fp64_tflops(int32_t device, double seconds) {
+  if (cudaSetDevice(device) != cudaSuccess) { fail(-7, "cudaSetDevice(%d) failed", device); return -1.0; }
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  double* sink = nullptr;
+  if (cudaMalloc(&sink, 8) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int blocks = sms * 8, threads = 256;
+  int iters = 2000;
+  dfma_peak_kernel<<<blocks, threads>>>(sink, iters, 1.0000001, 1e-9);   // warm-up
+  g_launches.fetch_add(1);
+  cudaDeviceSynchronize();
+  double best = 0.0, spent = 0.0;
+  while (spent < seconds) {
+    cudaEventRecord(e0);
+    dfma_peak_kernel<<<blocks, threads>>>(sink, iters, 1.0000001, 1e-9);
+    g_launches.fetch_add(1);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flop = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+    const double tf = flop / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+    spent += ms * 1e-3;
+    if (ms < 20.f) iters *= 2;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(sink);
+  return best;
+}
+
+int64_t gab1_kernel_launches(void) { return g_launches.load(); }
+
+int gab1_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+int gab1_version(void) { return GAB1_ABI_VERSION; }
+const char* gab1_last_error(void) { return g_err; }
+
+}  // extern "C"

@@ -1,0 +1,832 @@
+// solver_kernel.cuh — the hot path: explicit finite-difference time stepping of the EGFR/GRB2/GAB1/SHP2/SFK
+// reaction–diffusion model, one warp per parameter set, hand-written for sm_100a.
+//
+// Mapping.  Grid nodes 1..Nr (node 0 mirrors node 1 exactly because of the zero-flux condition, so it is never
+// stored) are dealt to the lanes of ONE warp in contiguous runs of K nodes; all ten cytosolic species of a node live
+// in that lane's registers for the whole solve.  Neighbour values cross lanes with two 64-bit shuffles per species per
+// step.  The membrane fixed point (Robin closures + eight membrane ODEs) runs lane-parallel: lanes 0-9 each own one
+// closure, lanes 10-17 one membrane species.  The time loop (3e4..2e6 steps) never touches global memory except for
+// the requested snapshot columns, which are staged through shared memory and stored fully coalesced.
+//
+// Two arithmetic modes (gab1_opts.arith):
+//   strict — every operation of the reference in source order with IEEE round-to-nearest intrinsics (never
+//            contracted); bit-identical to the CPU oracle; used to pin the control flow on the GPU.
+//   fast   — the product path: reciprocals hoisted, rate constants pre-scaled by dt, mass-action terms written as
+//            net fluxes, FMA contraction; agrees with strict to ~1e-13 relative (bound asserted in tests: 1e-9).
+//
+// Reference: basepdesolver.jl:149-296 (time loop), :150-180 (interior), :183-192 (r=0), :197-242 (membrane loop),
+// :265-295 (snapshots); basepdesolver_rect.jl:131-161; sapdesolver.jl:128-242; sapdesolver_memb-SFK.jl:175-222;
+// pulsechase_solver.jl:156-158.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "gab1pde.h"
+
+namespace gab1 {
+
+enum { iSFK, aSFK, GAB1, pGAB1, GRB2, G2G1, G2PG1, SHP2, PG1S, G2PG1S, NCY };   // basepdesolver.jl:199-202
+enum { mE, mES, mESmES, E, EG2, EG2G1, EG2PG1, EG2PG1S, NMB };                  // basepdesolver.jl:203
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int WS_HDR = 32;          // per-warp smem header: [0,16) interior-neighbour stage, [16,32) boundary stage
+constexpr int ML = 10;              // first membrane lane
+
+struct KernelArgs {
+  gab1_opts o;
+  long long S;
+  const double* Co; long long Co_stride;
+  const double* D; const double* k; const double* dt; const double* r;
+  double* out; long long out_stride;
+  int* status; int* n_saved; long long* n_steps; long long* n_bc;
+  const int* order;          // sets in descending-work order, or nullptr
+  unsigned int* counter;     // work queue head
+  double R_pow3;             // R^3.0 (libm pow on the host; sapdesolver.jl:353)
+  int P_pad;                 // doubles per staged row in shared memory
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// strict arithmetic: a double whose operators are single IEEE operations that ptxas may not contract
+struct sd {
+  double v;
+  __device__ __forceinline__ sd() {}
+  __device__ __forceinline__ sd(double x) : v(x) {}
+};
+__device__ __forceinline__ sd operator+(sd a, sd b) { return sd(__dadd_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator-(sd a, sd b) { return sd(__dsub_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator*(sd a, sd b) { return sd(__dmul_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator/(sd a, sd b) { return sd(__ddiv_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator-(sd a) { return sd(-a.v); }
+
+__device__ __forceinline__ double shfl(double x, int src) { return __shfl_sync(FULL, x, src); }
+__device__ __forceinline__ bool is_special(double x) {   // zero, Inf or NaN — decided on the bit pattern, off the FP64 pipe
+  const unsigned hi = (unsigned)__double2hiint(x) & 0x7fffffffu;
+  const unsigned lo = (unsigned)__double2loint(x);
+  return hi >= 0x7ff00000u || (hi | lo) == 0u;
+}
+
+// |1 - new/old| against tol exactly as the reference evaluates it (basepdesolver.jl:238-239).
+// 0: <= tol, 1: > tol, 2: NaN (Julia's maximum would return NaN).
+__device__ __forceinline__ int classify_exact(double oldv, double newv, double tol) {
+  const double e = fabs(__dsub_rn(1.0, __ddiv_rn(newv, oldv)));
+  return isnan(e) ? 2 : (e <= tol ? 0 : 1);
+}
+
+template <int K>
+struct Grid {          // per-lane constants of the radial grid, shared by every parameter set
+  double r[K];         // r_j of the lane's nodes
+  double a[K];         // strict: 1/(r_j*dr)                         (basepdesolver.jl:151)
+  double cp[K], cm[K]; // fast: 1/dr^2 +- 1/(r_j*dr); 0 on padding / boundary slots
+  int node[K];         // 1-based node number (Julia index j-1 .. i.e. node n is Julia's r[n+1])
+  bool interior[K];    // 1 <= node <= Nr-1
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Output writers (rare path).  Rows are staged in shared memory so that global stores are unit-stride.
+template <int K, typename F>
+__device__ __forceinline__ void stage_row(double* row, int lane, const Grid<K>& g, int Nr, F val) {
+#pragma unroll
+  for (int i = 0; i < K; ++i)
+    if (g.node[i] <= Nr) row[g.node[i]] = val(i);
+  if (lane == 0) row[0] = val(0);          // node 0 == node 1 (basepdesolver.jl:183-192)
+  __syncwarp();
+}
+__device__ __forceinline__ bool flush_row(double* dst, const double* row, int P, int lane) {
+  bool nan_seen = false;
+  for (int n = lane; n < P; n += 32) {
+    const double v = row[n];
+    nan_seen |= isnan(v);
+    dst[n] = v;
+  }
+  __syncwarp();
+  return __any_sync(FULL, nan_seen);
+}
+
+template <int K>
+__device__ __forceinline__ double species_at(const double (&u)[NCY][K], int q, int i) {
+  // q is a compile-time constant at every call site after unrolling
+  return u[q][i];
+}
+
+template <int K>
+__device__ __forceinline__ double derived_stot(const double (&u)[NCY][K], int i) {
+  return __dadd_rn(u[PG1S][i], u[G2PG1S][i]);                              // basepdesolver.jl:299
+}
+template <int K>
+__device__ __forceinline__ double derived_ptot(const double (&u)[NCY][K], int i, int form) {
+  if (form == GAB1_PG1TOT_VIA_STOT)                                        // basepdesolver.jl:300
+    return __dadd_rn(__dadd_rn(u[G2PG1][i], u[pGAB1][i]), derived_stot<K>(u, i));
+  return __dadd_rn(__dadd_rn(__dadd_rn(u[G2PG1][i], u[pGAB1][i]), u[PG1S][i]), u[G2PG1S][i]);   // basepdesolver_rect.jl:261
+}
+
+// one snapshot column of GAB1_OUT_FULL (basepdesolver.jl:268-294)
+template <int K>
+__device__ void write_full_column(const KernelArgs& a, double* oset, int c, const double (&u)[NCY][K],
+                                  const double (&m)[NMB], double t, double CoEGFR, int lane, const Grid<K>& g,
+                                  double* row, unsigned& status) {
+  const int Nr = a.o.Nr, P = Nr + 1;
+  const long long Cn = a.o.Nts + 1;
+  const unsigned mask = a.o.matrix_mask;
+  long long off = 0;
+  constexpr int kSpecies[10] = {iSFK, aSFK, GRB2, GAB1, SHP2, G2G1, G2PG1, G2PG1S, pGAB1, PG1S};   // basepdesolver.jl:271-280
+#pragma unroll
+  for (int mi = 0; mi < 12; ++mi) {
+    if (!((mask >> mi) & 1u)) continue;
+    if (mi < 10) {
+      const int q = kSpecies[mi];
+      stage_row<K>(row, lane, g, Nr, [&](int i) { return u[q][i]; });
+    } else if (mi == GAB1_M_PG1tot) {
+      stage_row<K>(row, lane, g, Nr, [&](int i) { return derived_ptot<K>(u, i, a.o.pg1tot_form); });
+    } else {
+      stage_row<K>(row, lane, g, Nr, [&](int i) { return derived_stot<K>(u, i); });
+    }
+    const bool nan_seen = flush_row(oset + off + (long long)c * P, row, P, lane);
+    if (mi == GAB1_M_PG1S && nan_seen) status |= GAB1_ST_NAN;
+    off += (long long)P * Cn;
+  }
+  if (!((mask >> GAB1_M_PG1S) & 1u)) {       // the NaN filter looks at PG1S whether or not it is materialised
+    bool ns = false;
+#pragma unroll
+    for (int i = 0; i < K; ++i) ns |= (g.node[i] <= Nr) && isnan(u[PG1S][i]);
+    if (__any_sync(FULL, ns)) status |= GAB1_ST_NAN;
+  }
+  if (lane == 0) {
+    double* v = oset + off;
+    const double Etot = __dmul_rn(2.0, __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(m[E], m[EG2]), m[EG2G1]), m[EG2PG1]), m[EG2PG1S]));  // :263
+    v[GAB1_V_pE * Cn + c] = __ddiv_rn(__dmul_rn(Etot, 100.0), CoEGFR);                     // :287
+    v[GAB1_V_mE * Cn + c] = m[mE];
+    v[GAB1_V_mES * Cn + c] = m[mES];
+    v[GAB1_V_mESmES * Cn + c] = m[mESmES];
+    v[GAB1_V_E * Cn + c] = m[E];
+    v[GAB1_V_EG2 * Cn + c] = m[EG2];
+    v[GAB1_V_EG2G1 * Cn + c] = m[EG2G1];
+    v[GAB1_V_EG2PG1 * Cn + c] = m[EG2PG1];
+    v[GAB1_V_EG2PG1S * Cn + c] = m[EG2PG1S];
+    v[GAB1_V_EGFR_SHP2 * Cn + c] = __ddiv_rn(__dmul_rn(m[EG2PG1S], 100.0), CoEGFR);        // basepdesolver_rect.jl:264
+    v[GAB1_V_t_out * Cn + c] = t;
+  }
+}
+
+// NumericalIntegration.integrate(r, y .* r.^2): trapezoid, left-to-right, on a staged row (every lane computes it)
+__device__ __forceinline__ double trapz_r2(const double* r, const double* y, int P) {
+  double acc = 0.0;
+  double yi = __dmul_rn(y[0], __dmul_rn(r[0], r[0]));
+  for (int i = 0; i + 1 < P; ++i) {
+    const double yn = __dmul_rn(y[i + 1], __dmul_rn(r[i + 1], r[i + 1]));
+    acc = __dadd_rn(acc, __dmul_rn(__dsub_rn(r[i + 1], r[i]), __dadd_rn(yi, yn)));
+    yi = yn;
+  }
+  return __dmul_rn(0.5, acc);
+}
+// R - minimum(r[y .>= f*maximum(y)])  (sapdesolver.jl:344-347)
+__device__ __forceinline__ double length_scale(const double* r, const double* y, int P, double f, double R, bool& threw) {
+  double mx = y[0];
+  bool nan_seen = isnan(y[0]);
+  for (int i = 1; i < P; ++i) {
+    if (isnan(y[i])) nan_seen = true;
+    else if (!(mx >= y[i])) mx = y[i];
+  }
+  if (nan_seen) mx = CUDART_NAN;
+  const double thr = __dmul_rn(f, mx);
+  for (int i = 0; i < P; ++i)
+    if (y[i] >= thr) return __dsub_rn(R, r[i]);
+  threw = true;
+  return 0.0;
+}
+
+// final-time outputs: FINAL4 (sapdesolver.jl:245-279), SIX (sapdesolver.jl:343-356), FINAL_STATE
+template <int K>
+__device__ void write_final(const KernelArgs& a, double* oset, const double (&u)[NCY][K], const double (&m)[NMB],
+                            int lane, const Grid<K>& g, double* rowA, double* rowB, unsigned& status) {
+  const int Nr = a.o.Nr, P = Nr + 1;
+  if (a.o.out_mode == GAB1_OUT_FINAL4) {
+    bool ns = false;
+    stage_row<K>(rowA, lane, g, Nr, [&](int i) { return u[iSFK][i]; });
+    ns |= flush_row(oset, rowA, P, lane);
+    stage_row<K>(rowA, lane, g, Nr, [&](int i) { return u[aSFK][i]; });
+    ns |= flush_row(oset + P, rowA, P, lane);
+    stage_row<K>(rowA, lane, g, Nr, [&](int i) { return derived_ptot<K>(u, i, a.o.pg1tot_form); });
+    ns |= flush_row(oset + 2 * P, rowA, P, lane);
+    stage_row<K>(rowA, lane, g, Nr, [&](int i) { return derived_stot<K>(u, i); });
+    ns |= flush_row(oset + 3 * P, rowA, P, lane);
+    if (ns) status |= GAB1_ST_NAN;
+  } else if (a.o.out_mode == GAB1_OUT_FINAL_STATE) {
+    bool ns = false;
+#pragma unroll
+    for (int q = 0; q < NCY; ++q) {
+      stage_row<K>(rowA, lane, g, Nr, [&](int i) { return u[q][i]; });
+      ns |= flush_row(oset + (long long)q * P, rowA, P, lane);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < NMB; ++j) { oset[(long long)NCY * P + j] = m[j]; ns |= isnan(m[j]); }
+    }
+    if (__any_sync(FULL, ns)) status |= GAB1_ST_NAN;
+  } else if (a.o.out_mode == GAB1_OUT_SIX) {
+    stage_row<K>(rowA, lane, g, Nr, [&](int i) { return u[aSFK][i]; });
+    stage_row<K>(rowB, lane, g, Nr, [&](int i) { return derived_stot<K>(u, i); });
+    bool threw = false;
+    double six[6];
+    const double R = a.o.R;
+    six[0] = length_scale(a.r, rowA, P, 0.5, R, threw);
+    six[1] = length_scale(a.r, rowA, P, 0.1, R, threw);
+    six[2] = length_scale(a.r, rowB, P, 0.5, R, threw);
+    six[3] = length_scale(a.r, rowB, P, 0.1, R, threw);
+    six[4] = __ddiv_rn(rowB[0], rowB[P - 1]);
+    six[5] = __ddiv_rn(__dmul_rn(trapz_r2(a.r, rowB, P), 3.0), a.R_pow3);
+    __syncwarp();
+    if (threw) status |= GAB1_ST_THROW;
+    bool ns = false;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const double v = threw ? 0.0 : six[i];
+      ns |= isnan(v);
+      if (lane == 0) oset[i] = v;
+    }
+    if (ns) status |= GAB1_ST_NAN;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Interior update, strict: the reference's expressions, term by term (basepdesolver.jl:151-179, rect :132-160)
+struct Rates {   // basepdesolver.jl:52-68
+  double kS2f, kS2r, kG1f, kG1r, kG2f, kG2r, kG1p, kG1dp, kSa, kSi, kp, kdp, kEGFf, kEGFr, EGF, kdf, kdr;
+};
+
+__device__ __forceinline__ void kinetics_strict(const sd (&L)[NCY], const double (&c)[NCY], const Rates& k, sd dt, double (&w)[NCY]) {
+  const sd Si = c[iSFK], Sa = c[aSFK], G1 = c[GAB1], pG1 = c[pGAB1], G2 = c[GRB2], g2g1 = c[G2G1], g2pg1 = c[G2PG1],
+           S2 = c[SHP2], pg1s = c[PG1S], g2pg1s = c[G2PG1S];
+  const sd kS2f = k.kS2f, kS2r = k.kS2r, kG1f = k.kG1f, kG1r = k.kG1r, kG1p = k.kG1p, kG1dp = k.kG1dp, kSi = k.kSi;
+  w[iSFK] = ((L[iSFK] + kSi * Sa) * dt + Si).v;
+  w[aSFK] = ((L[aSFK] - kSi * Sa) * dt + Sa).v;
+  w[GAB1] = ((L[GAB1] - kG1f * G1 * G2 + kG1r * g2g1 - kG1p * Sa * G1 + kG1dp * pG1) * dt + G1).v;
+  w[pGAB1] = ((L[pGAB1] - kG1f * pG1 * G2 + kG1r * g2pg1 + kG1p * Sa * G1 - kG1dp * pG1 - kS2f * S2 * pG1 + kS2r * pg1s) * dt + pG1).v;
+  w[GRB2] = ((L[GRB2] - kG1f * G1 * G2 + kG1r * g2g1 - kG1f * pG1 * G2 + kG1r * g2pg1 - kG1f * G2 * pg1s + kG1r * g2pg1s) * dt + G2).v;
+  w[G2G1] = ((L[G2G1] + kG1f * G1 * G2 - kG1r * g2g1 - kG1p * Sa * g2g1 + kG1dp * g2pg1) * dt + g2g1).v;
+  w[G2PG1] = ((L[G2PG1] + kG1f * pG1 * G2 - kG1r * g2pg1 + kG1p * Sa * g2g1 - kG1dp * g2pg1 - kS2f * S2 * g2pg1 + kS2r * g2pg1s) * dt + g2pg1).v;
+  w[SHP2] = ((L[SHP2] - kS2f * S2 * pG1 + kS2r * pg1s - kS2f * S2 * g2pg1 + kS2r * g2pg1s) * dt + S2).v;
+  w[PG1S] = ((L[PG1S] + kS2f * S2 * pG1 - kS2r * pg1s - kG1f * G2 * pg1s + kG1r * g2pg1s) * dt + pg1s).v;
+  w[G2PG1S] = ((L[G2PG1S] + kG1f * G2 * pg1s - kG1r * g2pg1s + kS2f * S2 * g2pg1 - kS2r * g2pg1s) * dt + g2pg1s).v;
+}
+
+// Membrane fixed point, strict, evaluated identically by every lane (basepdesolver.jl:197-242).
+// b[] holds the boundary values u[Nr+1,2]; m1/m2 the membrane columns [1]/[2]. Returns the iteration count.
+__device__ int membrane_strict(const KernelArgs& a, const Rates& k, double kp_now, const double (&Dsp)[NCY],
+                               const double (&In)[NCY], double (&b)[NCY], const double (&m1)[NMB], double (&m2)[NMB],
+                               double dt_, unsigned& status, bool& unconverged) {
+  const sd dr = a.o.dr, dt = dt_, one = 1.0, two = 2.0;
+  const sd kS2f = k.kS2f, kS2r = k.kS2r, kG1f = k.kG1f, kG1r = k.kG1r, kG2f = k.kG2f, kG2r = k.kG2r, kSa = k.kSa,
+           kp = kp_now, kdp = k.kdp, kEGFf = k.kEGFf, kEGFr = k.kEGFr, EGF = k.EGF, kdf = k.kdf, kdr = k.kdr;
+  const sd D_Si = Dsp[iSFK], D_Sa = Dsp[aSFK], D_G1 = Dsp[GAB1], D_G2 = Dsp[GRB2], D_G2G1 = Dsp[G2G1], D_S2 = Dsp[SHP2],
+           D_G1S2 = Dsp[PG1S], D_G2G1S2 = Dsp[G2PG1S];
+  const double tol = a.o.tol;
+  double err = __dmul_rn(tol, 2.0);
+  int it = 0;
+  unconverged = false;
+  for (;;) {
+    if (a.o.bc_loop == GAB1_BC_FOR_BREAK) { if (it >= a.o.maxiters) { unconverged = true; break; } }
+    else { if (!(err > tol)) break; if (it >= a.o.maxiters) { status |= GAB1_ST_ITER_CAP; break; } }
+    ++it;
+    double cold[NCY], mold[NMB];
+#pragma unroll
+    for (int q = 0; q < NCY; ++q) cold[q] = b[q];
+#pragma unroll
+    for (int j = 0; j < NMB; ++j) mold[j] = m2[j];
+    const sd mE2 = m2[E], mEG2 = m2[EG2], mEG2G1 = m2[EG2G1], mEG2PG1 = m2[EG2PG1], mEG2PG1S = m2[EG2PG1S];
+    const sd Etot = two * (mE2 + mEG2 + mEG2G1 + mEG2PG1 + mEG2PG1S);                                  // :205
+    const sd bi = sd(In[iSFK]) / (one + kSa * Etot * dr / D_Si);                                      // :206
+    const sd ba = sd(In[aSFK]) + kSa * bi * Etot * dr / D_Sa;                                         // :207
+    const sd bG1 = (kG1r * mEG2G1 * dr / D_G1 + sd(In[GAB1])) / (one + kG1f * mEG2 * dr / D_G1);      // :208
+    const sd bpG1 = (kG1r * mEG2PG1 * dr / D_G1 + sd(In[pGAB1])) / (one + kG1f * mEG2 * dr / D_G1);   // :209
+    const sd bG2 = (kG2r * mEG2 * dr / D_G2 + sd(In[GRB2])) / (one + kG2f * mE2 * dr / D_G2);         // :210
+    const sd bg2g1 = (kG2r * mEG2G1 * dr / D_G2G1 + sd(In[G2G1])) / (one + kG2f * mE2 * dr / D_G2G1); // :211
+    const sd bg2pg1 = (kG2r * mEG2PG1 * dr / D_G2G1 + sd(In[G2PG1])) / (one + kG2f * mE2 * dr / D_G2G1);            // :212
+    const sd bS2 = (kS2r * mEG2PG1S * dr / D_S2 + sd(In[SHP2])) / (one + kS2f * mEG2PG1 * dr / D_S2);               // :213
+    const sd bpg1s = (kG1r * mEG2PG1S * dr / D_G1S2 + sd(In[PG1S])) / (one + kG1f * mEG2 * dr / D_G1S2);            // :214
+    const sd bg2pg1s = (kG2r * mEG2PG1S * dr / D_G2G1S2 + sd(In[G2PG1S])) / (one + kG2f * mE2 * dr / D_G2G1S2);     // :215
+    b[iSFK] = bi.v; b[aSFK] = ba.v; b[GAB1] = bG1.v; b[pGAB1] = bpG1.v; b[GRB2] = bG2.v; b[G2G1] = bg2g1.v;
+    b[G2PG1] = bg2pg1.v; b[SHP2] = bS2.v; b[PG1S] = bpg1s.v; b[G2PG1S] = bg2pg1s.v;
+    const sd o_mE = m1[mE], o_mES = m1[mES], o_mm = m1[mESmES], o_E = m1[E], o_EG2 = m1[EG2], o_EG2G1 = m1[EG2G1],
+             o_EG2PG1 = m1[EG2PG1], o_EG2PG1S = m1[EG2PG1S];
+    m2[mE] = ((-kEGFf * EGF * o_mE + kEGFr * o_mES) * dt + o_mE).v;                                                  // :220
+    m2[mES] = ((kEGFf * EGF * o_mE - kEGFr * o_mES - two * kdf * o_mES * o_mES + two * kdr * o_mm) * dt + o_mES).v;  // :221
+    m2[mESmES] = ((kdf * o_mES * o_mES - kdr * o_mm - kp * o_mm + kdp * o_E) * dt + o_mm).v;                         // :222
+    m2[E] = ((kp * o_mm - kdp * o_E - kG2f * o_E * bG2 + kG2r * o_EG2 - kG2f * o_E * bg2g1 + kG2r * o_EG2G1
+              - kG2f * o_E * bg2pg1 + kG2r * o_EG2PG1 - kG2f * o_E * bg2pg1s + kG2r * o_EG2PG1S) * dt + o_E).v;      // :223-224
+    m2[EG2] = ((kG2f * bG2 * o_E - kG2r * o_EG2 - kG1f * bG1 * o_EG2 + kG1r * o_EG2G1 - kG1f * bpG1 * o_EG2
+                + kG1r * o_EG2PG1 - kG1f * bpg1s * o_EG2 + kG1r * o_EG2PG1S) * dt + o_EG2).v;                        // :225-226
+    m2[EG2G1] = ((kG2f * bg2g1 * o_E - kG2r * o_EG2G1 + kG1f * bG1 * o_EG2 - kG1r * o_EG2G1) * dt + o_EG2G1).v;      // :227
+    m2[EG2PG1] = ((kG2f * bg2pg1 * o_E - kG2r * o_EG2PG1 + kG1f * bpG1 * o_EG2 - kG1r * o_EG2PG1
+                   - kS2f * bS2 * o_EG2PG1 + kS2r * o_EG2PG1S) * dt + o_EG2PG1).v;                                   // :228-229
+    m2[EG2PG1S] = ((kS2f * bS2 * o_EG2PG1 - kS2r * o_EG2PG1S + kG1f * bpg1s * o_EG2 - kG1r * o_EG2PG1S
+                    + kG2f * bg2pg1s * o_E - kG2r * o_EG2PG1S) * dt + o_EG2PG1S).v;                                  // :230-231
+    // error = maximum(abs.(1 .- new./old)) with NaN propagation (:238)
+    double mx = -CUDART_INF;
+    bool nan_seen = false;
+#pragma unroll
+    for (int q = 0; q < NCY; ++q) {
+      const double e = fabs(__dsub_rn(1.0, __ddiv_rn(b[q], cold[q])));
+      if (isnan(e)) nan_seen = true; else if (e > mx) mx = e;
+    }
+#pragma unroll
+    for (int j = 0; j < NMB; ++j) {
+      const double e = fabs(__dsub_rn(1.0, __ddiv_rn(m2[j], mold[j])));
+      if (isnan(e)) nan_seen = true; else if (e > mx) mx = e;
+    }
+    err = nan_seen ? CUDART_NAN : mx;
+    if (a.o.bc_loop == GAB1_BC_FOR_BREAK && err <= tol) break;
+  }
+  return it;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-set driver.  u[q][i]: species q at the lane's i-th node.
+template <int K, bool STRICT>
+__device__ void solve_set(const KernelArgs& a, long long set, int lane, double* ws, const Grid<K>& g) {
+  const int Nr = a.o.Nr, P = Nr + 1, Nts = a.o.Nts, Cn = Nts + 1;
+  double* rowA = ws + WS_HDR;
+  double* rowB = rowA + a.P_pad;
+  double* oset = a.out + set * a.out_stride;
+  unsigned status = 0;
+
+  // ---- parameters of this set (uniform loads) ----
+  const double* Co = a.Co + set * a.Co_stride;
+  const double* Dv = a.D + set * GAB1_N_D;
+  const double* kv = a.k + set * GAB1_N_K;
+  const double dt = a.dt[set];
+  const double CoSFK = Co[0], CoG2 = Co[1], CoG1 = Co[2], CoS2 = Co[3], CoEGFR = Co[4];
+  Rates k;
+  k.kS2f = kv[0]; k.kS2r = kv[1]; k.kG1f = kv[2]; k.kG1r = kv[3]; k.kG2f = kv[4]; k.kG2r = kv[5]; k.kG1p = kv[6];
+  k.kG1dp = kv[7]; k.kSa = kv[8]; k.kSi = kv[9]; k.kp = kv[10]; k.kdp = kv[11]; k.kEGFf = kv[12]; k.kEGFr = kv[13];
+  k.EGF = kv[14]; k.kdf = kv[15]; k.kdr = kv[16];
+  double D_Si = Dv[0], D_Sa = Dv[0];
+  if (a.o.sfk_mode == GAB1_SFK_MEMBRANE) D_Sa = 1e-32;                                  // basepdesolver.jl:366
+  if (a.o.sfk_mode == GAB1_SFK_BOTH_FROZEN) { D_Si = 1e-32; D_Sa = 1e-32; }              // basepdesolver_rect.jl:305-306
+  const double Dsp[NCY] = {D_Si, D_Sa, Dv[4], Dv[4], Dv[1], Dv[2], Dv[2], Dv[6], Dv[5], Dv[3]};   // basepdesolver.jl:43-49
+
+  const bool track_t = (a.o.out_mode == GAB1_OUT_FULL || a.o.out_mode == GAB1_OUT_PCT_BOUND);
+  const long long nout = a.out_stride;
+
+  // the caller's block is already zero (host clears `out`): unsaved columns stay 0 like the reference's zeros(...)
+  (void)nout;
+
+  // Nt = Int64(ceil(tf/dt)) (basepdesolver.jl:72)
+  const double nt_f = ceil(__ddiv_rn(a.o.tf, dt));
+  if (!(nt_f >= 0.0 && nt_f < 9.0e18)) {
+    if (lane == 0) {
+      if (a.status) a.status[set] = GAB1_ST_THROW;
+      if (a.n_saved) a.n_saved[set] = 0;
+      if (a.n_steps) a.n_steps[set] = 0;
+      if (a.n_bc) a.n_bc[set] = 0;
+    }
+    return;
+  }
+  const long long Nt = (long long)nt_f;
+
+  // ---- state ----
+  double u[NCY][K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    const bool on = g.node[i] <= Nr;
+#pragma unroll
+    for (int q = 0; q < NCY; ++q) u[q][i] = 0.0;
+    u[iSFK][i] = on ? CoSFK : 0.0;      // basepdesolver.jl:137-140
+    u[GAB1][i] = on ? CoG1 : 0.0;
+    u[GRB2][i] = on ? CoG2 : 0.0;
+    u[SHP2][i] = on ? CoS2 : 0.0;
+  }
+  // where the boundary node Nr and its inner neighbour Nr-1 live
+  const int lane_b = (Nr - 1) / K, idx_b = (Nr - 1) % K;
+  const int lane_i = (Nr - 2) / K, idx_i = (Nr - 2) % K;
+
+  // initial column of the FULL output (basepdesolver.jl:94-97,111)
+  if (a.o.out_mode == GAB1_OUT_FULL) {
+    const unsigned mask = a.o.matrix_mask;
+    long long off = 0;
+    for (int mi = 0; mi < 12; ++mi) {
+      if (!((mask >> mi) & 1u)) continue;
+      const double v0 = mi == GAB1_M_iSFK ? CoSFK : mi == GAB1_M_GRB2 ? CoG2 : mi == GAB1_M_SHP2 ? CoS2 : mi == GAB1_M_GAB1 ? CoG1 : 0.0;
+      if (v0 != 0.0) for (int n = lane; n < P; n += 32) oset[off + n] = v0;
+      off += (long long)P * Cn;
+    }
+    if (lane == 0) oset[off + (long long)GAB1_V_mE * Cn] = CoEGFR;
+  }
+
+  double t = 0.0, t_save = a.o.dt_save;
+  int nts = 1;
+  const double modulus_step = (a.o.save_rule == GAB1_SAVE_MODULUS) ? rint(__ddiv_rn((double)Nt, (double)Nts)) : 0.0;
+  long long bc_total = 0;
+  double kp_now = k.kp;
+  double pct_ave = 0.0, pct_memb = 0.0;      // PCT_BOUND: from snapshot column Nts+1 (zeros if never written)
+  bool dead = false;                          // every state value is NaN: nothing can change any more
+  long long step = 1;
+
+  if constexpr (STRICT) {
+    // =========================================================================================== strict path
+    double b[NCY], m1[NMB], m2[NMB];
+#pragma unroll
+    for (int q = 0; q < NCY; ++q) b[q] = 0.0;             // u[Nr+1,2] starts at zero (basepdesolver.jl:115-124)
+#pragma unroll
+    for (int j = 0; j < NMB; ++j) { m1[j] = 0.0; m2[j] = 0.0; }
+    m1[mE] = CoEGFR;
+    const sd dr2 = __dmul_rn(a.o.dr, a.o.dr);
+    const sd sdt = dt;
+    for (; step <= Nt && !dead; ++step) {
+      if (a.o.t_prechase >= 0.0) {                        // pulsechase_solver.jl:156-158
+        if (__dadd_rn(a.o.t_prechase, dt) > t && t >= a.o.t_prechase) kp_now = 0.0;
+      }
+      double w[NCY][K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        sd L[NCY];
+        double c[NCY], wn[NCY];
+#pragma unroll
+        for (int q = 0; q < NCY; ++q) {
+          const double left = shfl(u[q][K - 1], lane - 1 < 0 ? 0 : lane - 1);
+          const double right = shfl(u[q][0], lane + 1 > 31 ? 31 : lane + 1);
+          const sd um = i > 0 ? u[q][i - 1] : (lane == 0 ? u[q][0] : left);
+          const sd up = i < K - 1 ? u[q][i + 1] : right;
+          const sd uc = u[q][i];
+          c[q] = uc.v;
+          if (a.o.geometry == GAB1_GEOM_SPHERICAL)
+            L[q] = sd(Dsp[q]) * (sd(g.a[i]) * (up - um) + (up - sd(2.0) * uc + um) / dr2);
+          else
+            L[q] = sd(Dsp[q]) * (up - sd(2.0) * uc + um) / dr2;
+        }
+        kinetics_strict(L, c, k, sdt, wn);
+#pragma unroll
+        for (int q = 0; q < NCY; ++q) w[q][i] = g.interior[i] ? wn[q] : u[q][i];
+      }
+      // inner-neighbour values of the boundary node, broadcast to every lane
+      double In[NCY];
+#pragma unroll
+      for (int q = 0; q < NCY; ++q) {
+        double v = 0.0;
+#pragma unroll
+        for (int i = 0; i < K; ++i) if (i == idx_i) v = w[q][i];
+        In[q] = shfl(v, lane_i);
+      }
+      bool unconverged;
+      const int it = membrane_strict(a, k, kp_now, Dsp, In, b, m1, m2, dt, status, unconverged);
+      bc_total += it;
+#pragma unroll
+      for (int q = 0; q < NCY; ++q) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) u[q][i] = (lane == lane_b && i == idx_b) ? b[q] : w[q][i];
+      }
+#pragma unroll
+      for (int j = 0; j < NMB; ++j) m1[j] = m2[j];
+      if (unconverged || isnan(m2[mE])) {
+        bool all_nan = true;
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+#pragma unroll
+          for (int q = 0; q < NCY; ++q) all_nan &= (g.node[i] > Nr) || isnan(u[q][i]);
+#pragma unroll
+        for (int j = 0; j < NMB; ++j) all_nan &= isnan(m2[j]);
+        dead = __all_sync(FULL, all_nan);
+      }
+      if (track_t) {
+        t = __dadd_rn(t, dt);
+        const bool save = a.o.save_rule == GAB1_SAVE_T_GE_TSAVE ? (t >= t_save) : (fmod((double)step, modulus_step) == 0.0);
+        if (save) {
+          if (nts >= Cn) status |= GAB1_ST_OVERFLOW;
+          else {
+            const int c = nts++;
+            if (a.o.out_mode == GAB1_OUT_FULL) write_full_column<K>(a, oset, c, u, m2, t, CoEGFR, lane, g, rowA, status);
+            else if (c == Cn - 1) {
+              stage_row<K>(rowA, lane, g, Nr, [&](int i) { return derived_stot<K>(u, i); });
+              pct_ave = trapz_r2(a.r, rowA, P);
+              pct_memb = m2[EG2PG1S];
+              __syncwarp();
+            }
+          }
+          if (a.o.save_rule == GAB1_SAVE_T_GE_TSAVE) t_save = __dadd_rn(t_save, a.o.dt_save);
+        }
+      }
+    }
+    // ---- all-NaN state: only the clock and the snapshot schedule still evolve ----
+    for (; step <= Nt; ++step) {
+      bc_total += (a.o.bc_loop == GAB1_BC_FOR_BREAK) ? a.o.maxiters : 1;
+      if (!track_t) { bc_total += (Nt - step) * (long long)((a.o.bc_loop == GAB1_BC_FOR_BREAK) ? a.o.maxiters : 1); break; }
+      t = __dadd_rn(t, dt);
+      const bool save = a.o.save_rule == GAB1_SAVE_T_GE_TSAVE ? (t >= t_save) : (fmod((double)step, modulus_step) == 0.0);
+      if (save) {
+        if (nts >= Cn) status |= GAB1_ST_OVERFLOW;
+        else {
+          const int c = nts++;
+          if (a.o.out_mode == GAB1_OUT_FULL) write_full_column<K>(a, oset, c, u, m2, t, CoEGFR, lane, g, rowA, status);
+          else if (c == Cn - 1) { pct_ave = CUDART_NAN; pct_memb = CUDART_NAN; }
+        }
+        if (a.o.save_rule == GAB1_SAVE_T_GE_TSAVE) t_save = __dadd_rn(t_save, a.o.dt_save);
+      }
+    }
+    if (Nt == 0) {      // no step taken: column 2 of every work array is still zero (sapdesolver.jl:245)
+#pragma unroll
+      for (int q = 0; q < NCY; ++q)
+#pragma unroll
+        for (int i = 0; i < K; ++i) u[q][i] = 0.0;
+    }
+    write_final<K>(a, oset, u, m2, lane, g, rowA, rowB, status);
+  } else {
+    // ============================================================================================= fast path
+    // ---- interior constants: rate constants and diffusivities pre-scaled by dt ----
+    const double kS2f_t = k.kS2f * dt, kS2r_t = k.kS2r * dt, kG1f_t = k.kG1f * dt, kG1r_t = k.kG1r * dt,
+                 kG1p_t = k.kG1p * dt, kG1dp_t = k.kG1dp * dt, kSi_t = k.kSi * dt;
+    const double inv_dr2 = 1.0 / (a.o.dr * a.o.dr);
+    const double c0 = -2.0 * inv_dr2;
+    const double Dt_Si = D_Si * dt, Dt_Sa = D_Sa * dt, Dt_G1 = Dv[4] * dt, Dt_G2 = Dv[1] * dt, Dt_G2G1 = Dv[2] * dt,
+                 Dt_S2 = Dv[6] * dt, Dt_G1S2 = Dv[5] * dt, Dt_G2G1S2 = Dv[3] * dt;
+
+    // ---- membrane block: lane roles ----
+    // lanes 0..9: Robin closure of cytosolic species `lane`; lanes 10..17: membrane species `lane-10`.
+    // closure q: (kr*M_num*dr/D + I)/(1 + kf*M_den*dr/D)   (basepdesolver.jl:206-215)
+    double kf = 0.0, kr = 0.0, Dq = 1.0;
+    int src_num = 0, src_den = 0;
+    switch (lane) {
+      case iSFK:   kf = k.kSa;  kr = 0.0;    Dq = D_Si;  break;                                        // den uses Etot
+      case aSFK:   kf = k.kSa;  kr = 0.0;    Dq = D_Si;  break;                                        // recomputes iSFK's closure
+      case GAB1:   kf = k.kG1f; kr = k.kG1r; Dq = Dv[4]; src_num = ML + EG2G1;   src_den = ML + EG2;    break;
+      case pGAB1:  kf = k.kG1f; kr = k.kG1r; Dq = Dv[4]; src_num = ML + EG2PG1;  src_den = ML + EG2;    break;
+      case GRB2:   kf = k.kG2f; kr = k.kG2r; Dq = Dv[1]; src_num = ML + EG2;     src_den = ML + E;      break;
+      case G2G1:   kf = k.kG2f; kr = k.kG2r; Dq = Dv[2]; src_num = ML + EG2G1;   src_den = ML + E;      break;
+      case G2PG1:  kf = k.kG2f; kr = k.kG2r; Dq = Dv[2]; src_num = ML + EG2PG1;  src_den = ML + E;      break;
+      case SHP2:   kf = k.kS2f; kr = k.kS2r; Dq = Dv[6]; src_num = ML + EG2PG1S; src_den = ML + EG2PG1; break;
+      case PG1S:   kf = k.kG1f; kr = k.kG1r; Dq = Dv[5]; src_num = ML + EG2PG1S; src_den = ML + EG2;    break;
+      case G2PG1S: kf = k.kG2f; kr = k.kG2r; Dq = Dv[3]; src_num = ML + EG2PG1S; src_den = ML + E;      break;
+      default: break;
+    }
+    const double drD = a.o.dr / Dq;
+    const double cr = kr * drD, cf = kf * drD;
+    const double ca = k.kSa * (a.o.dr / D_Sa);            // aSFK closure coefficient; a true division (D_Sa may be 1e-32)
+    const bool is_flux = lane >= GAB1 && lane <= G2PG1S;   // this closure's net binding flux feeds the membrane ODEs
+    const double kf_t = is_flux ? kf * dt : 0.0, kr_t = is_flux ? kr * dt : 0.0;
+    // membrane species j (lane 10+j): new = base + sum of signed fluxes held by closure lanes (basepdesolver.jl:220-231
+    // regrouped by reaction: every binding term appears once with each sign)
+    int fs0 = 0, fs1 = 0, fs2 = 0, fs3 = 0;                // source lanes (lane 0 holds a zero flux)
+    unsigned neg = 0;                                      // bit i: subtract source i
+    switch (lane - ML) {
+      case E:       fs0 = GRB2;   fs1 = G2G1;  fs2 = G2PG1; fs3 = G2PG1S; neg = 0xF; break;
+      case EG2:     fs0 = GRB2;   fs1 = GAB1;  fs2 = pGAB1; fs3 = PG1S;   neg = 0xE; break;
+      case EG2G1:   fs0 = G2G1;   fs1 = GAB1;  break;
+      case EG2PG1:  fs0 = G2PG1;  fs1 = pGAB1; fs2 = SHP2;  neg = 0x4; break;
+      case EG2PG1S: fs0 = G2PG1S; fs1 = PG1S;  fs2 = SHP2;  break;
+      default: break;
+    }
+    // membrane-only reactions (old-time values only): f_j = alpha*m_j*y - beta*m_{j+1} on lanes 10,11,12
+    //   lane 10: EGF binding  kEGFf*EGF*mE - kEGFr*mES        lane 11: dimerisation kdf*mES^2 - kdr*mESmES
+    //   lane 12: phosphorylation kp*mESmES - kdp*E
+    double alpha = 0.0, beta = 0.0;
+    switch (lane - ML) {
+      case mE:     alpha = k.kEGFf * k.EGF; beta = k.kEGFr; break;
+      case mES:    alpha = k.kdf;           beta = k.kdr;   break;
+      case mESmES: alpha = kp_now;          beta = k.kdp;   break;
+      default: break;
+    }
+    const double tol = a.o.tol;
+    // x: the value this lane tracks across iterations and steps — boundary value u[Nr+1] of species `lane`
+    // (lanes 0..9) or membrane species lane-10 (lanes 10..17)
+    double x = (lane == ML + mE) ? CoEGFR : 0.0;
+    double Etot_prev = 0.0;                                // 2*(E+EG2+EG2G1+EG2PG1+EG2PG1S) at the old time level
+
+    for (; step <= Nt && !dead; ++step) {
+      if (a.o.t_prechase >= 0.0) {                         // pulsechase_solver.jl:156-158
+        if (a.o.t_prechase + dt > t && t >= a.o.t_prechase) { kp_now = 0.0; if (lane == ML + mESmES) alpha = 0.0; }
+      }
+      // ---- interior: D*lap + kinetics, explicit Euler (basepdesolver.jl:150-180) ----
+      double w[NCY][K];
+      {
+        double hl[NCY], hr[NCY];
+#pragma unroll
+        for (int q = 0; q < NCY; ++q) {
+          const double l = __shfl_up_sync(FULL, u[q][K - 1], 1);
+          hl[q] = lane == 0 ? u[q][0] : l;
+          hr[q] = __shfl_down_sync(FULL, u[q][0], 1);
+        }
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          double lap[NCY];
+#pragma unroll
+          for (int q = 0; q < NCY; ++q) {
+            const double um = i > 0 ? u[q][i - 1] : hl[q];
+            const double up = i < K - 1 ? u[q][i + 1] : hr[q];
+            lap[q] = fma(g.cp[i], up, fma(g.cm[i], um, c0 * u[q][i]));
+          }
+          const double Si = u[iSFK][i], Sa = u[aSFK][i], G1 = u[GAB1][i], pG1 = u[pGAB1][i], G2 = u[GRB2][i],
+                       g2g1 = u[G2G1][i], g2pg1 = u[G2PG1][i], S2 = u[SHP2][i], pg1s = u[PG1S][i], g2pg1s = u[G2PG1S][i];
+          const double gb = kG1f_t * G2, ph = kG1p_t * Sa, sb = kS2f_t * S2;
+          const double v1 = fma(gb, G1, -(kG1r_t * g2g1));        // GRB2 + GAB1   <-> G2G1
+          const double v3 = fma(gb, pG1, -(kG1r_t * g2pg1));      // GRB2 + pGAB1  <-> G2PG1
+          const double v5 = fma(gb, pg1s, -(kG1r_t * g2pg1s));    // GRB2 + PG1S   <-> G2PG1S
+          const double v2 = fma(ph, G1, -(kG1dp_t * pG1));        // GAB1  <-> pGAB1 (aSFK / phosphatase)
+          const double v6 = fma(ph, g2g1, -(kG1dp_t * g2pg1));    // G2G1  <-> G2PG1
+          const double v4 = fma(sb, pG1, -(kS2r_t * pg1s));       // SHP2 + pGAB1  <-> PG1S
+          const double v7 = fma(sb, g2pg1, -(kS2r_t * g2pg1s));   // SHP2 + G2PG1  <-> G2PG1S
+          const double v8 = kSi_t * Sa;                           // aSFK -> iSFK
+          w[iSFK][i] = fma(Dt_Si, lap[iSFK], Si + v8);
+          w[aSFK][i] = fma(Dt_Sa, lap[aSFK], Sa - v8);
+          w[GAB1][i] = fma(Dt_G1, lap[GAB1], G1 - v1 - v2);
+          w[pGAB1][i] = fma(Dt_G1, lap[pGAB1], pG1 - v3 + v2 - v4);
+          w[GRB2][i] = fma(Dt_G2, lap[GRB2], G2 - v1 - v3 - v5);
+          w[G2G1][i] = fma(Dt_G2G1, lap[G2G1], g2g1 + v1 - v6);
+          w[G2PG1][i] = fma(Dt_G2G1, lap[G2PG1], g2pg1 + v3 + v6 - v7);
+          w[SHP2][i] = fma(Dt_S2, lap[SHP2], S2 - v4 - v7);
+          w[PG1S][i] = fma(Dt_G1S2, lap[PG1S], pg1s + v4 - v5);
+          w[G2PG1S][i] = fma(Dt_G2G1S2, lap[G2PG1S], g2pg1s + v5 + v7);
+        }
+      }
+      // ---- hand the inner-neighbour values u+[Nr-1] to the closure lanes ----
+      if (lane == lane_i) {
+#pragma unroll
+        for (int q = 0; q < NCY; ++q) {
+          double v = w[q][0];
+#pragma unroll
+          for (int i = 1; i < K; ++i) if (i == idx_i) v = w[q][i];
+          ws[q] = v;
+        }
+      }
+      __syncwarp();
+      const double Iq = lane < NCY ? ws[lane == aSFK ? iSFK : lane] : 0.0;
+      const double Ia = ws[aSFK];
+
+      // ---- membrane block prologue: everything that depends only on old-time values ----
+      const double m_old = x;                                       // lanes >= 10: membrane value at the old time level
+      const double m_next = __shfl_down_sync(FULL, m_old, 1);
+      const bool f_lane = lane >= ML + mE && lane <= ML + mESmES;
+      const double f = f_lane ? alpha * m_old * (lane == ML + mES ? m_old : 1.0) - beta * m_next : 0.0;
+      const double f_prev = __shfl_up_sync(FULL, f, 1);
+      const double dm = lane == ML + mE ? -f : lane == ML + mES ? f_prev - 2.0 * f : lane == ML + mESmES ? f_prev - f
+                        : lane == ML + E ? f_prev : 0.0;
+      const double base = fma(dt, dm, m_old);
+      const double f3 = shfl(f, ML + mESmES);
+      const double Etot_new = fma(2.0 * dt, f3, Etot_prev);         // all binding fluxes cancel in the sum of E-species
+      const double Md_old = shfl(m_old, src_den), Mn_old = shfl(m_old, src_num);
+      const double A_t = is_flux ? kf_t * Md_old : 0.0;             // flux = dt*(kf*M_den*b - kr*M_num), old-time M
+      const double B_t = is_flux ? kr_t * Mn_old : 0.0;
+
+      // ---- fixed-point iterations (basepdesolver.jl:197-242) ----
+      int it = 0;
+      double Et = Etot_prev;                                        // first pass sees last step's membrane values
+      bool go = true, unconverged = false, nan_exit = false;
+      if (a.o.bc_loop == GAB1_BC_FOR_BREAK && a.o.maxiters <= 0) go = false;
+      while (go) {
+        ++it;
+        const double Mn = shfl(x, src_num);
+        double Md = shfl(x, src_den);
+        if (lane < GAB1) Md = Et;
+        const double qv = (lane < GAB1 ? Iq : fma(cr, Mn, Iq)) / fma(cf, Md, 1.0);
+        const double bnew = lane == aSFK ? fma(ca * Et, qv, Ia) : qv;
+        const double F = is_flux ? fma(A_t, bnew, -B_t) : 0.0;
+        double F0 = shfl(F, fs0), F1 = shfl(F, fs1), F2 = shfl(F, fs2), F3 = shfl(F, fs3);
+        F0 = (neg & 1u) ? -F0 : F0; F1 = (neg & 2u) ? -F1 : F1; F2 = (neg & 4u) ? -F2 : F2; F3 = (neg & 8u) ? -F3 : F3;
+        const double mnew = base + F0 + F1 + F2 + F3;
+        const double xnew = lane < NCY ? bnew : mnew;
+        // convergence: |1 - new/old| <= tol for all 18 tracked values, NaN-aware
+        int cls;
+        const bool tracked = lane < ML + NMB;
+        const bool special = tracked && (is_special(x) || is_special(xnew));
+        if (__any_sync(FULL, special)) {
+          cls = tracked ? classify_exact(x, xnew, tol) : 0;
+        } else {
+          cls = (tracked && !(fabs(x - xnew) <= tol * fabs(x))) ? 1 : 0;
+        }
+        x = tracked ? xnew : 0.0;
+        Et = Etot_new;
+        const bool any_nan = __any_sync(FULL, cls == 2);
+        const bool all_ok = __all_sync(FULL, cls == 0);
+        if (a.o.bc_loop == GAB1_BC_FOR_BREAK) {
+          if (all_ok && !any_nan) go = false;
+          else if (it >= a.o.maxiters) { go = false; unconverged = true; }
+        } else {
+          if (any_nan || all_ok) { go = false; nan_exit = any_nan; }   // `while error > tol`: NaN leaves the loop
+          else if (it >= a.o.maxiters) { go = false; status |= GAB1_ST_ITER_CAP; }
+        }
+      }
+      bc_total += it;
+      Etot_prev = Etot_new;
+      // ---- boundary values back to the lane that owns node Nr ----
+      if (lane < NCY) ws[16 + lane] = x;
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < NCY; ++q) {
+        const double bq = ws[16 + q];
+#pragma unroll
+        for (int i = 0; i < K; ++i) u[q][i] = (lane == lane_b && i == idx_b) ? bq : w[q][i];
+      }
+      if (unconverged || nan_exit) {
+        bool all_nan = (lane < ML || lane >= ML + NMB) || isnan(x);
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+#pragma unroll
+          for (int q = 0; q < NCY; ++q) all_nan &= (g.node[i] > Nr) || isnan(u[q][i]);
+        dead = __all_sync(FULL, all_nan);
+      }
+      if (track_t) {
+        t = t + dt;
+        const bool save = a.o.save_rule == GAB1_SAVE_T_GE_TSAVE ? (t >= t_save) : (fmod((double)step, modulus_step) == 0.0);
+        if (save) {
+          if (nts >= Cn) status |= GAB1_ST_OVERFLOW;
+          else {
+            const int c = nts++;
+            double m[NMB];
+#pragma unroll
+            for (int j = 0; j < NMB; ++j) m[j] = shfl(x, ML + j);
+            if (a.o.out_mode == GAB1_OUT_FULL) write_full_column<K>(a, oset, c, u, m, t, CoEGFR, lane, g, rowA, status);
+            else if (c == Cn - 1) {
+              stage_row<K>(rowA, lane, g, Nr, [&](int i) { return derived_stot<K>(u, i); });
+              pct_ave = trapz_r2(a.r, rowA, P);
+              pct_memb = m[EG2PG1S];
+              __syncwarp();
+            }
+          }
+          if (a.o.save_rule == GAB1_SAVE_T_GE_TSAVE) t_save = t_save + a.o.dt_save;
+        }
+      }
+    }
+    double m[NMB];
+#pragma unroll
+    for (int j = 0; j < NMB; ++j) m[j] = shfl(x, ML + j);
+    // ---- all-NaN state: only the clock and the snapshot schedule still evolve ----
+    for (; step <= Nt; ++step) {
+      const long long per = (a.o.bc_loop == GAB1_BC_FOR_BREAK) ? a.o.maxiters : 1;
+      if (!track_t) { bc_total += (Nt - step + 1) * per; break; }
+      bc_total += per;
+      t = t + dt;
+      const bool save = a.o.save_rule == GAB1_SAVE_T_GE_TSAVE ? (t >= t_save) : (fmod((double)step, modulus_step) == 0.0);
+      if (save) {
+        if (nts >= Cn) status |= GAB1_ST_OVERFLOW;
+        else {
+          const int c = nts++;
+          if (a.o.out_mode == GAB1_OUT_FULL) write_full_column<K>(a, oset, c, u, m, t, CoEGFR, lane, g, rowA, status);
+          else if (c == Cn - 1) { pct_ave = CUDART_NAN; pct_memb = CUDART_NAN; }
+        }
+        if (a.o.save_rule == GAB1_SAVE_T_GE_TSAVE) t_save = t_save + a.o.dt_save;
+      }
+    }
+    if (Nt == 0) {
+#pragma unroll
+      for (int q = 0; q < NCY; ++q)
+#pragma unroll
+        for (int i = 0; i < K; ++i) u[q][i] = 0.0;
+#pragma unroll
+      for (int j = 0; j < NMB; ++j) m[j] = 0.0;
+    }
+    write_final<K>(a, oset, u, m, lane, g, rowA, rowB, status);
+  }
+
+  if (a.o.out_mode == GAB1_OUT_PCT_BOUND) {      // run_base_model.jl:272-276
+    const double R = a.o.R;
+    const double ave = __ddiv_rn(__dmul_rn(pct_ave, 3.0), __dmul_rn(__dmul_rn(R, R), R));
+    const double mem = __ddiv_rn(__dmul_rn(pct_memb, a.o.pct_mul), a.o.pct_div);
+    const double pct = __dmul_rn(__ddiv_rn(__dadd_rn(ave, mem), CoG1), 100.0);
+    if (isnan(pct)) status |= GAB1_ST_NAN;
+    if (lane == 0) oset[0] = pct;
+  }
+  if (track_t && nts < Cn) status |= GAB1_ST_SHORT;
+  if (lane == 0) {
+    if (a.status) a.status[set] = (int)status;
+    if (a.n_saved) a.n_saved[set] = track_t ? nts : 0;
+    if (a.n_steps) a.n_steps[set] = Nt;
+    if (a.n_bc) a.n_bc[set] = bc_total;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent kernel: every warp pulls parameter sets from a queue ordered by descending work.
+template <int K, bool STRICT>
+__global__ void __launch_bounds__(128) solve_kernel(const KernelArgs a) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* ws = smem + (size_t)warp * (WS_HDR + 2 * a.P_pad);
+  const int Nr = a.o.Nr;
+
+  Grid<K> g;
+  {
+    const double dr = a.o.dr;
+    const double inv_dr2 = 1.0 / (dr * dr);
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      const int n = lane * K + 1 + i;
+      g.node[i] = n;
+      g.interior[i] = n <= Nr - 1;
+      const double r = n <= Nr ? a.r[n] : 1.0;
+      g.r[i] = r;
+      g.a[i] = __ddiv_rn(1.0, __dmul_rn(r, dr));
+      const double aj = (a.o.geometry == GAB1_GEOM_SPHERICAL) ? 1.0 / (r * dr) : 0.0;
+      g.cp[i] = g.interior[i] ? inv_dr2 + aj : 0.0;
+      g.cm[i] = g.interior[i] ? inv_dr2 - aj : 0.0;
+    }
+  }
+  for (;;) {
+    unsigned item = 0;
+    if (lane == 0) item = atomicAdd(a.counter, 1u);
+    item = __shfl_sync(FULL, item, 0);
+    if ((long long)item >= a.S) break;
+    const long long set = a.order ? (long long)a.order[item] : (long long)item;
+    solve_set<K, STRICT>(a, set, lane, ws, g);
+    __syncwarp();
+  }
+}
+
+}  // namespace gab1

@@ -1,0 +1,240 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Needs a B200: run with -m gpu.
+
+Two bars (north_star: relative tolerance 1e-9 in FP64):
+  * arith = strict  -> BIT-IDENTICAL to the oracle, including iteration counts and snapshot schedule;
+  * arith = fast    -> |gpu - ref| <= RTOL * max(|ref|, 1e-6 * max|field|) with RTOL = 1e-9, and identical
+                       membrane-iteration counts, step counts and snapshot schedules (the data-dependent control flow).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def gfe(pkg):
+    import __graft_entry__ as g
+    g.build()
+    lib = pkg.abi.load_library()
+    assert lib.gab1_device_count() >= 1, "no CUDA device: the product path has no CPU fallback"
+    return pkg.host.Frontend(pkg.abi.CudaBackend(arith=pkg.abi.ARITH_FAST))
+
+
+@pytest.fixture(scope="module")
+def sfe(pkg, gfe):
+    return pkg.host.Frontend(pkg.abi.CudaBackend(arith=pkg.abi.ARITH_STRICT))
+
+
+def assert_bits(a, b, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    same = (a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b))
+    assert same.all(), f"{what}: {np.count_nonzero(~same)}/{same.size} values differ, first at {np.argwhere(~same)[0]}"
+
+
+def rel_err(a, b):
+    """max over sets of |a-b| / max(|b|, 1e-6*max|b| per set); NaN positions must coincide."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN pattern differs"
+    fin = np.isfinite(b)
+    scale = np.where(fin, np.abs(b), 0).max(axis=-1, keepdims=True)
+    den = np.maximum(np.abs(b), 1e-6 * scale)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        e = np.where(fin & (den > 0), np.abs(a - b) / den, 0.0)
+    return float(e.max())
+
+
+def check_control_flow(res, ref):
+    np.testing.assert_array_equal(res.n_steps, ref.n_steps)
+    np.testing.assert_array_equal(res.n_saved, ref.n_saved)
+    np.testing.assert_array_equal(res.n_bc_iters, ref.n_bc_iters)
+    np.testing.assert_array_equal(res.status, ref.status)
+
+
+VARIANTS = {
+    "pdesolver": dict(),
+    "membSFK": dict(sfk_mode=1),
+    "rect": dict(geometry=1, pg1tot_form=1),
+    "rect_frozen_modulus": dict(geometry=1, pg1tot_form=1, sfk_mode=2, save_rule=1),
+    "pulsechase": dict(t_prechase=0.2),
+    "fitting_mask": dict(matrices=("aSFK", "PG1S", "G2PG1S")),
+}
+
+
+@pytest.mark.parametrize("dr", [0.4, 0.2, 0.1, 0.05])
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_strict_is_bit_identical_full(pkg, sfe, ofe, ensemble, variant, dr):
+    """All four lane layouts (K = 1, 2, 4, 8 nodes per lane) and every solver variant, full snapshot output."""
+    Co = pkg.params.base_Co()
+    rows = [0, 1, 2, 3, 75]
+    tf = {0.4: 0.3, 0.2: 0.3, 0.1: 0.1, 0.05: 0.03}[dr]
+    kw = dict(dr=dr, tf=tf, Nts=6, tol=1e-4, maxiters=20, **VARIANTS[variant])
+    res = sfe.pdesolver_batch(Co, ensemble[rows, :7], ensemble[rows, 7:], **kw)
+    ref = ofe.pdesolver_batch(Co, ensemble[rows, :7], ensemble[rows, 7:], **kw)
+    check_control_flow(res, ref)
+    assert_bits(res.out, ref.out, f"{variant} dr={dr}")
+
+
+@pytest.mark.parametrize("dr", [0.4, 0.2, 0.1, 0.05])
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_fast_within_tolerance_full(pkg, gfe, ofe, ensemble, variant, dr):
+    Co = pkg.params.base_Co()
+    rows = [0, 1, 2, 3, 4]
+    tf = {0.4: 0.6, 0.2: 0.5, 0.1: 0.2, 0.05: 0.05}[dr]
+    kw = dict(dr=dr, tf=tf, Nts=8, tol=1e-4, maxiters=20, **VARIANTS[variant])
+    res = gfe.pdesolver_batch(Co, ensemble[rows, :7], ensemble[rows, 7:], **kw)
+    ref = ofe.pdesolver_batch(Co, ensemble[rows, :7], ensemble[rows, 7:], **kw)
+    check_control_flow(res, ref)
+    e = rel_err(res.out, ref.out)
+    assert e < RTOL, f"{variant} dr={dr}: rel err {e:.3e}"
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+@pytest.mark.parametrize("membSFK", [False, True])
+def test_final_time_outputs(pkg, gfe, sfe, ofe, ensemble, membSFK, arith):
+    """sapdesolver / sapdesolver_membSFK final profiles, the six GSA scalars and the full final state (config 3/4 path)."""
+    fe = sfe if arith == "strict" else gfe
+    Co = pkg.params.hela_Co() if membSFK else pkg.params.base_Co()
+    rows = list(range(10, 26))
+    for mode in (pkg.abi.OUT_FINAL4, pkg.abi.OUT_SIX, pkg.abi.OUT_FINAL_STATE):
+        kw = dict(dr=0.2, tf=1.0, membSFK=membSFK, out_mode=mode)
+        res = fe.sapdesolver_batch(Co, ensemble[rows, :7], ensemble[rows, 7:], **kw)
+        ref = ofe.sapdesolver_batch(Co, ensemble[rows, :7], ensemble[rows, 7:], **kw)
+        check_control_flow(res, ref)
+        if arith == "strict":
+            assert_bits(res.out, ref.out, f"mode {mode}")
+        elif mode == pkg.abi.OUT_SIX:
+            # length scales are grid-quantised: must be identical; ratio and average within tolerance
+            np.testing.assert_array_equal(res.out[:, :4], ref.out[:, :4])
+            assert rel_err(res.out[:, 4:], ref.out[:, 4:]) < RTOL
+        else:
+            assert rel_err(res.out, ref.out) < RTOL
+
+
+def test_full_length_solves_config2_sample(pkg, gfe, ofe, ensemble):
+    """BASELINE config 2 settings (run_ensemble defaults: dr=0.2, tf=5, Nts=100, tol=1e-4, maxit=20) on a sample that
+    includes a diverging set (row 75): ~3.7e4 steps each, every snapshot compared."""
+    Co = pkg.params.base_Co()
+    rows = [0, 1, 2, 75, 333, 4999, 2500, 1234]
+    kw = dict(dr=0.2, tol=1e-4, maxiters=20)
+    res = gfe.pdesolver_batch(Co, ensemble[rows, :7], ensemble[rows, 7:], **kw)
+    ref = ofe.pdesolver_batch(Co, ensemble[rows, :7], ensemble[rows, 7:], **kw)
+    np.testing.assert_array_equal(res.n_steps, ref.n_steps)
+    np.testing.assert_array_equal(res.n_saved, ref.n_saved)
+    good = (ref.status & pkg.abi.ST_NAN) == 0
+    assert list(good) == [True, True, True, False, False, True, True, True]
+    np.testing.assert_array_equal(res.status & pkg.abi.ST_NAN, ref.status & pkg.abi.ST_NAN)
+    np.testing.assert_array_equal(res.n_bc_iters[good], ref.n_bc_iters[good])
+    e = rel_err(res.out[good], ref.out[good])
+    assert e < RTOL, f"rel err {e:.3e}"
+
+
+def test_single_solve_config1(pkg, gfe, sfe, ofe):
+    """BASELINE config 1: run_base_model.jl:83 — pdesolver(Co, Diffs, kvals; R, dr=0.1, tf=5, Nts=100, tol=1e-2)."""
+    Co, D, k = pkg.params.base_Co(), pkg.params.DIFFS_BASE, pkg.params.KVALS_BASE
+    sol_r, r_r, t_r, dt_r = ofe.pdesolver(Co, D, k, dr=0.1, tol=1e-2)
+    sol_g, r_g, t_g, dt_g = gfe.pdesolver(Co, D, k, dr=0.1, tol=1e-2)
+    assert dt_g == dt_r and np.array_equal(t_g, t_r) and np.array_equal(r_g, r_r)
+    for name in sol_r._fields:
+        e = rel_err(getattr(sol_g, name).T, getattr(sol_r, name).T)
+        assert e < RTOL, f"{name}: {e:.3e}"
+    sol_s = sfe.pdesolver(Co, D, k, dr=0.1, tol=1e-2)[0]
+    for name in sol_r._fields:
+        assert_bits(np.ascontiguousarray(getattr(sol_s, name)), np.ascontiguousarray(getattr(sol_r, name)), name)
+
+
+def test_golden_kat(pkg, gfe, sfe, ensemble):
+    """Committed known-answer vectors (tests/golden/oracle_kat.npz, written by the oracle in the build container)."""
+    from pathlib import Path
+    kat = np.load(Path(__file__).parent / "golden" / "oracle_kat.npz")
+    sub = ensemble[kat["rows"]]
+    Co = pkg.params.base_Co()
+    calls = [
+        ("full_dr04_tf1", lambda fe: fe.pdesolver_batch(Co, sub[:, :7], sub[:, 7:], dr=0.4, tf=1.0, Nts=10, tol=1e-4, maxiters=20)),
+        ("final4_dr02_tf05", lambda fe: fe.sapdesolver_batch(Co, sub[:, :7], sub[:, 7:], dr=0.2, tf=0.5)),
+        ("final4_memb_dr02_tf05", lambda fe: fe.sapdesolver_batch(pkg.params.hela_Co(), sub[:, :7], sub[:, 7:], dr=0.2, tf=0.5, membSFK=True)),
+        ("six_dr02_tf05", lambda fe: fe.sapdesolver_batch(Co, sub[:, :7], sub[:, 7:], dr=0.2, tf=0.5, out_mode=pkg.abi.OUT_SIX)),
+        ("full_rect_dr025_tf05", lambda fe: fe.pdesolver_batch(Co, sub[:, :7], sub[:, 7:], dr=0.25, tf=0.5, Nts=5, tol=1e-4,
+                                                              maxiters=20, geometry=pkg.abi.GEOM_RECT, pg1tot_form=pkg.abi.PG1TOT_CHAIN)),
+    ]
+    for name, call in calls:
+        assert_bits(call(sfe).out, kat[name], name)
+        if name.startswith("six"):
+            np.testing.assert_array_equal(call(gfe).out[:, :4], kat[name][:, :4])
+        else:
+            assert rel_err(call(gfe).out, kat[name]) < RTOL, name
+    np.testing.assert_array_equal(calls[0][1](gfe).n_bc_iters, kat["full_dr04_tf1_nbc"])
+
+
+def test_pct_bound_and_julia_surface(pkg, gfe, ofe, ensemble):
+    Co = pkg.params.base_Co()
+    pct_g, _ = gfe.pct_shp2_bound_gab1(Co, ensemble[:32, :7], ensemble[:32, 7:])
+    pct_r, _ = ofe.pct_shp2_bound_gab1(Co, ensemble[:32, :7], ensemble[:32, 7:])
+    assert rel_err(pct_g[None], pct_r[None]) < RTOL
+    assert abs(pct_g[0] - 23.46) < 0.01 and abs(pct_g[1] - 26.05) < 0.01          # SURVEY.md §4 probe values
+    # fbatch_dk_mt semantics: log-space 24 x S in, 6 x S out, zeros(6) for a column that throws (sapdesolver.jl:371-387)
+    pb = np.log(ensemble[70:80].T)
+    out_g = gfe.fbatch_dk_mt(pb, tf=2.0)
+    out_r = ofe.fbatch_dk_mt(pb, tf=2.0)
+    assert out_g.shape == (6, 10)
+    np.testing.assert_array_equal(out_g[:4], out_r[:4])
+    assert rel_err(out_g[4:].T, out_r[4:].T) < RTOL
+    # run_ensemble drops NaN sets and keeps 1-based indices (get_param_posteriors.jl:155-161)
+    rows_g = gfe.run_ensemble("pdesolver", ensemble[74:77], Co, Nts=10)
+    assert [x.index for x in rows_g] == [1, 3]
+    assert rows_g[0].sol.PG1S.shape == (51, 11) and rows_g[0].t_sol.shape == (11,)
+
+
+def test_edge_cases(pkg, gfe, sfe, ofe, ensemble):
+    Co = pkg.params.base_Co()
+    D, k = ensemble[:3, :7], ensemble[:3, 7:]
+    # empty batch
+    res = gfe.pdesolver_batch(Co, np.zeros((0, 7)), np.zeros((0, 17)), dr=0.4, tf=0.1, Nts=2)
+    assert res.out.shape[0] == 0
+    # per-set Co (S x 5), ragged work (very different dt per set), a dt so large that no snapshot is due (SHORT)
+    Cos = np.stack([Co, pkg.params.hela_Co(), Co * 0.5])
+    dt = np.array([1e-4, 3e-4, 2.5e-3])
+    kw = dict(dr=0.4, tf=0.2, Nts=4, dt=dt, tol=1e-4, maxiters=20)
+    res, ref = sfe.pdesolver_batch(Cos, D, k, **kw), ofe.pdesolver_batch(Cos, D, k, **kw)
+    check_control_flow(res, ref)
+    assert_bits(res.out, ref.out)
+    # dt_save smaller than dt: more snapshots are due than columns exist (OVERFLOW), identical handling
+    kw = dict(dr=0.4, tf=0.05, Nts=40, dt_save=1e-5, tol=1e-4, maxiters=20)
+    res, ref = sfe.pdesolver_batch(Co, D, k, **kw), ofe.pdesolver_batch(Co, D, k, **kw)
+    assert (ref.status & pkg.abi.ST_OVERFLOW).all()
+    check_control_flow(res, ref)
+    assert_bits(res.out, ref.out)
+    # unusable dt -> the reference throws InexactError; reported per set, zeros written
+    kw = dict(dr=0.4, tf=0.05, Nts=4, dt=np.array([0.0, np.nan, 1e-4]))
+    res, ref = gfe.pdesolver_batch(Co, D, k, **kw), ofe.pdesolver_batch(Co, D, k, **kw)
+    assert list(res.status[:2] & pkg.abi.ST_THROW) == [pkg.abi.ST_THROW] * 2 and not res.out[:2].any()
+    np.testing.assert_array_equal(res.status, ref.status)
+    # maxiters = 0: the membrane loop body never runs
+    kw = dict(dr=0.4, tf=0.05, Nts=4, maxiters=0)
+    res, ref = sfe.pdesolver_batch(Co, D, k, **kw), ofe.pdesolver_batch(Co, D, k, **kw)
+    assert_bits(res.out, ref.out)
+    assert rel_err(gfe.pdesolver_batch(Co, D, k, **kw).out, ref.out) < RTOL
+    # largest grid one warp holds: Nr = 250 (R = 100, dr = 0.4; length_scale_estimates.jl:55-56)
+    kw = dict(R=100.0, dr=0.4, tf=0.05, Nts=2, tol=1e-4, maxiters=20)
+    res, ref = sfe.pdesolver_batch(pkg.params.base_Co(100.0), D, k, **kw), ofe.pdesolver_batch(pkg.params.base_Co(100.0), D, k, **kw)
+    check_control_flow(res, ref)
+    assert_bits(res.out, ref.out)
+
+
+def test_whole_ensemble_properties_config2(pkg, gfe, ensemble):
+    """All 5000 rows of parameter_ensemble.csv at config-2 settings; size-independent properties only:
+    exactly the 33 diverging rows the oracle finds, EGFR conservation and SFK conservation on the rest."""
+    Co = pkg.params.base_Co()
+    res = gfe.pdesolver_batch(Co, ensemble[:, :7], ensemble[:, 7:], dr=0.2, tol=1e-4, maxiters=20,
+                              out_mode=pkg.abi.OUT_FINAL_STATE)
+    bad = np.nonzero(res.status & pkg.abi.ST_NAN)[0]
+    assert len(bad) == 33 and bad[0] == 75 and bad[-1] == 4656          # SURVEY.md §6 (33/5000), oracle run in DESIGN.md
+    good = res.out[(res.status & pkg.abi.ST_NAN) == 0]
+    P = 51
+    m = good[:, 10 * P:]
+    tot = m[:, 0] + m[:, 1] + 2 * m[:, 2:].sum(axis=1)
+    assert np.abs(tot / Co[4] - 1).max() < 1e-11
+    assert np.abs((good[:, :P] + good[:, P:2 * P]) / Co[0] - 1).max() < 1e-11
+    ratio = res.n_bc_iters / res.n_steps
+    assert 1.4 < np.median(ratio) < 1.6                                 # 1.51 measured with the oracle
