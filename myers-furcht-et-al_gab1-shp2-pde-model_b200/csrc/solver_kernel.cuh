@@ -704,6 +704,7 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
         }
       }
       bc_total += it;
+      if (it == 0 && lane >= ML) x = 0.0;   // maxiters = 0: column [2] of the membrane arrays is never written (stays zero)
       Etot_prev = Etot_new;
       // ---- boundary values back to the lane that owns node Nr ----
       if (lane < NCY) ws[16 + lane] = x;
