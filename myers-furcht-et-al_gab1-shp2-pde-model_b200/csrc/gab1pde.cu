@@ -96,13 +96,13 @@ size_t carve(Workspace& w, void* base, long long S) {
   return off;
 }
 
-template <int K, bool STRICT>
+template <int K, int MODE>
 int launch(const gab1::KernelArgs& args, int device, cudaStream_t stream) {
   static std::mutex mu;
   static int blocks_per_sm[64] = {0};
   static int sms[64] = {0};
   const size_t smem = (size_t)4 * (gab1::WS_HDR + 2 * (size_t)args.P_pad) * sizeof(double);
-  auto kern = gab1::solve_kernel<K, STRICT>;
+  auto kern = gab1::solve_kernel<K, MODE>;
   {
     std::lock_guard<std::mutex> lk(mu);
     if (device < 64 && blocks_per_sm[device] == 0) {
@@ -170,13 +170,19 @@ int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long 
     CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp, bytes, w.keys_in, w.keys_out, w.vals_in, w.vals_out,
                                                        (int)S, 0, 32, stream));
   }
-  const bool strict = o->arith == 1;
+  const int mode = o->arith == 1 ? gab1::MODE_STRICT : (o->bc_loop == GAB1_BC_WHILE ? gab1::MODE_FAST_WHILE : gab1::MODE_FAST_FOR);
+#define GAB1_LAUNCH(KK)                                                                          \
+  case KK:                                                                                       \
+    return mode == gab1::MODE_STRICT       ? launch<KK, gab1::MODE_STRICT>(a, device, stream)     \
+           : mode == gab1::MODE_FAST_WHILE ? launch<KK, gab1::MODE_FAST_WHILE>(a, device, stream) \
+                                           : launch<KK, gab1::MODE_FAST_FOR>(a, device, stream);
   switch (K) {
-    case 1: return strict ? launch<1, true>(a, device, stream) : launch<1, false>(a, device, stream);
-    case 2: return strict ? launch<2, true>(a, device, stream) : launch<2, false>(a, device, stream);
-    case 4: return strict ? launch<4, true>(a, device, stream) : launch<4, false>(a, device, stream);
-    case 8: return strict ? launch<8, true>(a, device, stream) : launch<8, false>(a, device, stream);
+    GAB1_LAUNCH(1)
+    GAB1_LAUNCH(2)
+    GAB1_LAUNCH(4)
+    GAB1_LAUNCH(8)
   }
+#undef GAB1_LAUNCH
   return fail(-6, "no kernel for K=%d", K);
 }
 

@@ -73,23 +73,29 @@ __device__ __forceinline__ int classify_exact(double oldv, double newv, double t
   return isnan(e) ? 2 : (e <= tol ? 0 : 1);
 }
 
+// Layout: the warp's 32*K slots are RIGHT-aligned on the grid, so that the boundary node Nr is always the last slot of
+// lane G-1 (G = ceil(Nr/K)) and its inner neighbour the slot before it — compile-time register indices.  Slots left
+// of node 1 are padding that stays zero.
 template <int K>
 struct Grid {          // per-lane constants of the radial grid, shared by every parameter set
-  double r[K];         // r_j of the lane's nodes
   double a[K];         // strict: 1/(r_j*dr)                         (basepdesolver.jl:151)
-  double cp[K], cm[K]; // fast: 1/dr^2 +- 1/(r_j*dr); 0 on padding / boundary slots
-  int node[K];         // 1-based node number (Julia index j-1 .. i.e. node n is Julia's r[n+1])
+  double cp[K], cm[K], c0[K];   // fast: lap = cp*u[j+1] + cm*u[j-1] + c0*u[j]; node 1 folds its mirror u[0]=u[1] into c0;
+                                // all three are 0 on padding and on the boundary slot
+  int node[K];         // node number: node n is Julia's index n+1; valid nodes are 1..Nr
   bool interior[K];    // 1 <= node <= Nr-1
+  int G;               // lanes in use
 };
 
 // ---------------------------------------------------------------------------------------------------------------
 // Output writers (rare path).  Rows are staged in shared memory so that global stores are unit-stride.
 template <int K, typename F>
 __device__ __forceinline__ void stage_row(double* row, int lane, const Grid<K>& g, int Nr, F val) {
+  (void)lane;
 #pragma unroll
-  for (int i = 0; i < K; ++i)
-    if (g.node[i] <= Nr) row[g.node[i]] = val(i);
-  if (lane == 0) row[0] = val(0);          // node 0 == node 1 (basepdesolver.jl:183-192)
+  for (int i = 0; i < K; ++i) {
+    if (g.node[i] >= 1 && g.node[i] <= Nr) row[g.node[i]] = val(i);
+    if (g.node[i] == 1) row[0] = val(i);   // node 0 == node 1 (basepdesolver.jl:183-192)
+  }
   __syncwarp();
 }
 __device__ __forceinline__ bool flush_row(double* dst, const double* row, int P, int lane) {
@@ -148,7 +154,7 @@ __device__ void write_full_column(const KernelArgs& a, double* oset, int c, cons
   if (!((mask >> GAB1_M_PG1S) & 1u)) {       // the NaN filter looks at PG1S whether or not it is materialised
     bool ns = false;
 #pragma unroll
-    for (int i = 0; i < K; ++i) ns |= (g.node[i] <= Nr) && isnan(u[PG1S][i]);
+    for (int i = 0; i < K; ++i) ns |= (g.node[i] >= 1 && g.node[i] <= Nr) && isnan(u[PG1S][i]);
     if (__any_sync(FULL, ns)) status |= GAB1_ST_NAN;
   }
   if (lane == 0) {
@@ -342,8 +348,24 @@ __device__ int membrane_strict(const KernelArgs& a, const Rates& k, double kp_no
 
 // ---------------------------------------------------------------------------------------------------------------
 // Per-set driver.  u[q][i]: species q at the lane's i-th node.
-template <int K, bool STRICT>
+// MODE 0: fast arithmetic, `for ... break` membrane loop; 1: fast arithmetic, `while error > tol` loop; 2: strict.
+enum { MODE_FAST_FOR = 0, MODE_FAST_WHILE = 1, MODE_STRICT = 2 };
+
+__device__ __forceinline__ double fast_div(double a, double b) {
+  // reciprocal seed + two Newton steps + one residual correction: <= 1 ulp for normal operands, no slow-path branch
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
+
+template <int K, int MODE>
 __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* ws, const Grid<K>& g) {
+  constexpr bool STRICT = MODE == MODE_STRICT;
   const int Nr = a.o.Nr, P = Nr + 1, Nts = a.o.Nts, Cn = Nts + 1;
   double* rowA = ws + WS_HDR;
   double* rowB = rowA + a.P_pad;
@@ -388,7 +410,7 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
   double u[NCY][K];
 #pragma unroll
   for (int i = 0; i < K; ++i) {
-    const bool on = g.node[i] <= Nr;
+    const bool on = g.node[i] >= 1 && g.node[i] <= Nr;
 #pragma unroll
     for (int q = 0; q < NCY; ++q) u[q][i] = 0.0;
     u[iSFK][i] = on ? CoSFK : 0.0;      // basepdesolver.jl:137-140
@@ -397,8 +419,10 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
     u[SHP2][i] = on ? CoS2 : 0.0;
   }
   // where the boundary node Nr and its inner neighbour Nr-1 live
-  const int lane_b = (Nr - 1) / K, idx_b = (Nr - 1) % K;
-  const int lane_i = (Nr - 2) / K, idx_i = (Nr - 2) % K;
+  const int lane_b = g.G - 1;
+  constexpr int idx_b = K - 1;
+  const int lane_i = K >= 2 ? g.G - 1 : g.G - 2;
+  constexpr int idx_i = K >= 2 ? K - 2 : 0;
 
   // initial column of the FULL output (basepdesolver.jl:94-97,111)
   if (a.o.out_mode == GAB1_OUT_FULL) {
@@ -445,7 +469,7 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
         for (int q = 0; q < NCY; ++q) {
           const double left = shfl(u[q][K - 1], lane - 1 < 0 ? 0 : lane - 1);
           const double right = shfl(u[q][0], lane + 1 > 31 ? 31 : lane + 1);
-          const sd um = i > 0 ? u[q][i - 1] : (lane == 0 ? u[q][0] : left);
+          const sd um = g.node[i] == 1 ? u[q][i] : (i > 0 ? u[q][i - 1] : left);
           const sd up = i < K - 1 ? u[q][i + 1] : right;
           const sd uc = u[q][i];
           c[q] = uc.v;
@@ -482,7 +506,7 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
 #pragma unroll
         for (int i = 0; i < K; ++i)
 #pragma unroll
-          for (int q = 0; q < NCY; ++q) all_nan &= (g.node[i] > Nr) || isnan(u[q][i]);
+          for (int q = 0; q < NCY; ++q) all_nan &= (g.node[i] < 1) || isnan(u[q][i]);
 #pragma unroll
         for (int j = 0; j < NMB; ++j) all_nan &= isnan(m2[j]);
         dead = __all_sync(FULL, all_nan);
@@ -531,22 +555,23 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
     write_final<K>(a, oset, u, m2, lane, g, rowA, rowB, status);
   } else {
     // ============================================================================================= fast path
+    constexpr bool WHILE = MODE == MODE_FAST_WHILE;
     // ---- interior constants: rate constants and diffusivities pre-scaled by dt ----
     const double kS2f_t = k.kS2f * dt, kS2r_t = k.kS2r * dt, kG1f_t = k.kG1f * dt, kG1r_t = k.kG1r * dt,
                  kG1p_t = k.kG1p * dt, kG1dp_t = k.kG1dp * dt, kSi_t = k.kSi * dt;
-    const double inv_dr2 = 1.0 / (a.o.dr * a.o.dr);
-    const double c0 = -2.0 * inv_dr2;
     const double Dt_Si = D_Si * dt, Dt_Sa = D_Sa * dt, Dt_G1 = Dv[4] * dt, Dt_G2 = Dv[1] * dt, Dt_G2G1 = Dv[2] * dt,
                  Dt_S2 = Dv[6] * dt, Dt_G1S2 = Dv[5] * dt, Dt_G2G1S2 = Dv[3] * dt;
 
     // ---- membrane block: lane roles ----
-    // lanes 0..9: Robin closure of cytosolic species `lane`; lanes 10..17: membrane species `lane-10`.
-    // closure q: (kr*M_num*dr/D + I)/(1 + kf*M_den*dr/D)   (basepdesolver.jl:206-215)
+    // lanes 0..9   Robin closure of cytosolic species `lane`:  b = (cr*M_num + I)/(1 + cf*M_den)   (basepdesolver.jl:206-215)
+    // lanes 10..17 membrane species `lane-10`;  lane 18 carries Etot = 2(E+EG2+EG2G1+EG2PG1+EG2PG1S) as a pseudo-species
+    // lane 31      always holds zeros: the source of every unused shuffle
+    constexpr int LZ = 31, LE = ML + NMB;
     double kf = 0.0, kr = 0.0, Dq = 1.0;
-    int src_num = 0, src_den = 0;
+    int src_num = LZ, src_den = LZ;
     switch (lane) {
-      case iSFK:   kf = k.kSa;  kr = 0.0;    Dq = D_Si;  break;                                        // den uses Etot
-      case aSFK:   kf = k.kSa;  kr = 0.0;    Dq = D_Si;  break;                                        // recomputes iSFK's closure
+      case iSFK:   kf = k.kSa;  Dq = D_Si; src_den = LE; break;                     // I/(1 + kSa*Etot*dr/D_S)
+      case aSFK:   kf = k.kSa;  Dq = D_Si; src_num = LE; src_den = LE; break;       // rewritten over the same denominator, see cr_a
       case GAB1:   kf = k.kG1f; kr = k.kG1r; Dq = Dv[4]; src_num = ML + EG2G1;   src_den = ML + EG2;    break;
       case pGAB1:  kf = k.kG1f; kr = k.kG1r; Dq = Dv[4]; src_num = ML + EG2PG1;  src_den = ML + EG2;    break;
       case GRB2:   kf = k.kG2f; kr = k.kG2r; Dq = Dv[1]; src_num = ML + EG2;     src_den = ML + E;      break;
@@ -558,61 +583,73 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
       default: break;
     }
     const double drD = a.o.dr / Dq;
-    const double cr = kr * drD, cf = kf * drD;
+    const double cf = kf * drD;
+    const double cr_fixed = kr * drD;
     const double ca = k.kSa * (a.o.dr / D_Sa);            // aSFK closure coefficient; a true division (D_Sa may be 1e-32)
     const bool is_flux = lane >= GAB1 && lane <= G2PG1S;   // this closure's net binding flux feeds the membrane ODEs
     const double kf_t = is_flux ? kf * dt : 0.0, kr_t = is_flux ? kr * dt : 0.0;
-    // membrane species j (lane 10+j): new = base + sum of signed fluxes held by closure lanes (basepdesolver.jl:220-231
-    // regrouped by reaction: every binding term appears once with each sign)
-    int fs0 = 0, fs1 = 0, fs2 = 0, fs3 = 0;                // source lanes (lane 0 holds a zero flux)
-    unsigned neg = 0;                                      // bit i: subtract source i
+    // membrane species j: new = base + sum_i sg_i * F[fs_i], F = dt*(kf*M_den*b - kr*M_num) held by the closure lanes
+    // (basepdesolver.jl:220-231 regrouped by reaction: every binding term appears once with each sign)
+    int fs0 = LZ, fs1 = LZ, fs2 = LZ, fs3 = LZ;
+    double sg0 = 0.0, sg1 = 0.0, sg2 = 0.0, sg3 = 0.0;
     switch (lane - ML) {
-      case E:       fs0 = GRB2;   fs1 = G2G1;  fs2 = G2PG1; fs3 = G2PG1S; neg = 0xF; break;
-      case EG2:     fs0 = GRB2;   fs1 = GAB1;  fs2 = pGAB1; fs3 = PG1S;   neg = 0xE; break;
-      case EG2G1:   fs0 = G2G1;   fs1 = GAB1;  break;
-      case EG2PG1:  fs0 = G2PG1;  fs1 = pGAB1; fs2 = SHP2;  neg = 0x4; break;
-      case EG2PG1S: fs0 = G2PG1S; fs1 = PG1S;  fs2 = SHP2;  break;
+      case E:       fs0 = GRB2;   fs1 = G2G1;  fs2 = G2PG1; fs3 = G2PG1S; sg0 = -1.0; sg1 = -1.0; sg2 = -1.0; sg3 = -1.0; break;
+      case EG2:     fs0 = GRB2;   fs1 = GAB1;  fs2 = pGAB1; fs3 = PG1S;   sg0 = 1.0;  sg1 = -1.0; sg2 = -1.0; sg3 = -1.0; break;
+      case EG2G1:   fs0 = G2G1;   fs1 = GAB1;  sg0 = 1.0; sg1 = 1.0; break;
+      case EG2PG1:  fs0 = G2PG1;  fs1 = pGAB1; fs2 = SHP2; sg0 = 1.0; sg1 = 1.0; sg2 = -1.0; break;
+      case EG2PG1S: fs0 = G2PG1S; fs1 = PG1S;  fs2 = SHP2; sg0 = 1.0; sg1 = 1.0; sg2 = 1.0; break;
       default: break;
     }
-    // membrane-only reactions (old-time values only): f_j = alpha*m_j*y - beta*m_{j+1} on lanes 10,11,12
-    //   lane 10: EGF binding  kEGFf*EGF*mE - kEGFr*mES        lane 11: dimerisation kdf*mES^2 - kdr*mESmES
-    //   lane 12: phosphorylation kp*mESmES - kdp*E
-    double alpha = 0.0, beta = 0.0;
+    // membrane-only reactions, old-time values: f = m*(alpha + alpha2*m) - beta*m_next on lanes 10,11,12
+    //   lane 10: kEGFf*EGF*mE - kEGFr*mES     lane 11: kdf*mES^2 - kdr*mESmES     lane 12: kp*mESmES - kdp*E
+    // and their contribution to d(m)/dt: dm = s_own*f + s_src*f[f_src]   (lane 18: dEtot/dt = 2*f3, all bindings cancel)
+    double alpha = 0.0, alpha2 = 0.0, beta = 0.0, s_own = 0.0, s_src = 0.0;
+    int f_src = LZ;
     switch (lane - ML) {
-      case mE:     alpha = k.kEGFf * k.EGF; beta = k.kEGFr; break;
-      case mES:    alpha = k.kdf;           beta = k.kdr;   break;
-      case mESmES: alpha = kp_now;          beta = k.kdp;   break;
+      case mE:     alpha = k.kEGFf * k.EGF; beta = k.kEGFr; s_own = -1.0; break;
+      case mES:    alpha2 = k.kdf;          beta = k.kdr;   s_own = -2.0; s_src = 1.0; f_src = ML + mE; break;
+      case mESmES: alpha = kp_now;          beta = k.kdp;   s_own = -1.0; s_src = 1.0; f_src = ML + mES; break;
+      case E:      s_src = 1.0; f_src = ML + mESmES; break;
+      case NMB:    s_src = 2.0; f_src = ML + mESmES; break;
       default: break;
     }
     const double tol = a.o.tol;
+    const bool untracked = lane >= LE;
+    const int iq_idx = lane < NCY ? lane : 10;             // ws[10..15] stay zero
+    const bool pulse = a.o.t_prechase >= 0.0;
+    const int maxiters = a.o.maxiters;
     // x: the value this lane tracks across iterations and steps — boundary value u[Nr+1] of species `lane`
-    // (lanes 0..9) or membrane species lane-10 (lanes 10..17)
+    // (lanes 0..9), membrane species lane-10 (lanes 10..17), Etot (lane 18), zero elsewhere
     double x = (lane == ML + mE) ? CoEGFR : 0.0;
-    double Etot_prev = 0.0;                                // 2*(E+EG2+EG2G1+EG2PG1+EG2PG1S) at the old time level
 
     for (; step <= Nt && !dead; ++step) {
-      if (a.o.t_prechase >= 0.0) {                         // pulsechase_solver.jl:156-158
+      if (pulse) {                                         // pulsechase_solver.jl:156-158
         if (a.o.t_prechase + dt > t && t >= a.o.t_prechase) { kp_now = 0.0; if (lane == ML + mESmES) alpha = 0.0; }
       }
-      // ---- interior: D*lap + kinetics, explicit Euler (basepdesolver.jl:150-180) ----
-      double w[NCY][K];
+      // ---- interior: D*lap + kinetics, explicit Euler, updated in place (basepdesolver.jl:150-180) ----
       {
         double hl[NCY], hr[NCY];
 #pragma unroll
         for (int q = 0; q < NCY; ++q) {
-          const double l = __shfl_up_sync(FULL, u[q][K - 1], 1);
-          hl[q] = lane == 0 ? u[q][0] : l;
+          hl[q] = __shfl_up_sync(FULL, u[q][K - 1], 1);
           hr[q] = __shfl_down_sync(FULL, u[q][0], 1);
+        }
+        double L[2][NCY];     // Laplacians of the node being updated and of the next one (which still needs old values)
+#pragma unroll
+        for (int q = 0; q < NCY; ++q) {
+          const double up = K > 1 ? u[q][1] : hr[q];
+          L[0][q] = fma(g.cp[0], up, fma(g.cm[0], hl[q], g.c0[0] * u[q][0]));
         }
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-          double lap[NCY];
+          if (i + 1 < K) {
 #pragma unroll
-          for (int q = 0; q < NCY; ++q) {
-            const double um = i > 0 ? u[q][i - 1] : hl[q];
-            const double up = i < K - 1 ? u[q][i + 1] : hr[q];
-            lap[q] = fma(g.cp[i], up, fma(g.cm[i], um, c0 * u[q][i]));
+            for (int q = 0; q < NCY; ++q) {
+              const double up = i + 2 < K ? u[q][i + 2] : hr[q];
+              L[(i + 1) & 1][q] = fma(g.cp[i + 1], up, fma(g.cm[i + 1], u[q][i], g.c0[i + 1] * u[q][i + 1]));
+            }
           }
+          const double(&lap)[NCY] = L[i & 1];
           const double Si = u[iSFK][i], Sa = u[aSFK][i], G1 = u[GAB1][i], pG1 = u[pGAB1][i], G2 = u[GRB2][i],
                        g2g1 = u[G2G1][i], g2pg1 = u[G2PG1][i], S2 = u[SHP2][i], pg1s = u[PG1S][i], g2pg1s = u[G2PG1S][i];
           const double gb = kG1f_t * G2, ph = kG1p_t * Sa, sb = kS2f_t * S2;
@@ -623,104 +660,88 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
           const double v6 = fma(ph, g2g1, -(kG1dp_t * g2pg1));    // G2G1  <-> G2PG1
           const double v4 = fma(sb, pG1, -(kS2r_t * pg1s));       // SHP2 + pGAB1  <-> PG1S
           const double v7 = fma(sb, g2pg1, -(kS2r_t * g2pg1s));   // SHP2 + G2PG1  <-> G2PG1S
-          const double v8 = kSi_t * Sa;                           // aSFK -> iSFK
-          w[iSFK][i] = fma(Dt_Si, lap[iSFK], Si + v8);
-          w[aSFK][i] = fma(Dt_Sa, lap[aSFK], Sa - v8);
-          w[GAB1][i] = fma(Dt_G1, lap[GAB1], G1 - v1 - v2);
-          w[pGAB1][i] = fma(Dt_G1, lap[pGAB1], pG1 - v3 + v2 - v4);
-          w[GRB2][i] = fma(Dt_G2, lap[GRB2], G2 - v1 - v3 - v5);
-          w[G2G1][i] = fma(Dt_G2G1, lap[G2G1], g2g1 + v1 - v6);
-          w[G2PG1][i] = fma(Dt_G2G1, lap[G2PG1], g2pg1 + v3 + v6 - v7);
-          w[SHP2][i] = fma(Dt_S2, lap[SHP2], S2 - v4 - v7);
-          w[PG1S][i] = fma(Dt_G1S2, lap[PG1S], pg1s + v4 - v5);
-          w[G2PG1S][i] = fma(Dt_G2G1S2, lap[G2PG1S], g2pg1s + v5 + v7);
+          u[iSFK][i] = fma(Dt_Si, lap[iSFK], fma(kSi_t, Sa, Si));             // aSFK -> iSFK
+          u[aSFK][i] = fma(Dt_Sa, lap[aSFK], fma(-kSi_t, Sa, Sa));
+          u[GAB1][i] = fma(Dt_G1, lap[GAB1], G1 - v1 - v2);
+          u[pGAB1][i] = fma(Dt_G1, lap[pGAB1], pG1 - v3 + v2 - v4);
+          u[GRB2][i] = fma(Dt_G2, lap[GRB2], G2 - v1 - v3 - v5);
+          u[G2G1][i] = fma(Dt_G2G1, lap[G2G1], g2g1 + v1 - v6);
+          u[G2PG1][i] = fma(Dt_G2G1, lap[G2PG1], g2pg1 + v3 + v6 - v7);
+          u[SHP2][i] = fma(Dt_S2, lap[SHP2], S2 - v4 - v7);
+          u[PG1S][i] = fma(Dt_G1S2, lap[PG1S], pg1s + v4 - v5);
+          u[G2PG1S][i] = fma(Dt_G2G1S2, lap[G2PG1S], g2pg1s + v5 + v7);
         }
       }
       // ---- hand the inner-neighbour values u+[Nr-1] to the closure lanes ----
       if (lane == lane_i) {
 #pragma unroll
-        for (int q = 0; q < NCY; ++q) {
-          double v = w[q][0];
-#pragma unroll
-          for (int i = 1; i < K; ++i) if (i == idx_i) v = w[q][i];
-          ws[q] = v;
-        }
+        for (int q = 0; q < NCY; ++q) ws[q] = u[q][idx_i];
       }
       __syncwarp();
-      const double Iq = lane < NCY ? ws[lane == aSFK ? iSFK : lane] : 0.0;
-      const double Ia = ws[aSFK];
+      const double Iq = ws[iq_idx];
 
       // ---- membrane block prologue: everything that depends only on old-time values ----
-      const double m_old = x;                                       // lanes >= 10: membrane value at the old time level
+      const double m_old = x;                                        // lanes >= 10: value at the old time level
       const double m_next = __shfl_down_sync(FULL, m_old, 1);
-      const bool f_lane = lane >= ML + mE && lane <= ML + mESmES;
-      const double f = f_lane ? alpha * m_old * (lane == ML + mES ? m_old : 1.0) - beta * m_next : 0.0;
-      const double f_prev = __shfl_up_sync(FULL, f, 1);
-      const double dm = lane == ML + mE ? -f : lane == ML + mES ? f_prev - 2.0 * f : lane == ML + mESmES ? f_prev - f
-                        : lane == ML + E ? f_prev : 0.0;
-      const double base = fma(dt, dm, m_old);
-      const double f3 = shfl(f, ML + mESmES);
-      const double Etot_new = fma(2.0 * dt, f3, Etot_prev);         // all binding fluxes cancel in the sum of E-species
-      const double Md_old = shfl(m_old, src_den), Mn_old = shfl(m_old, src_num);
-      const double A_t = is_flux ? kf_t * Md_old : 0.0;             // flux = dt*(kf*M_den*b - kr*M_num), old-time M
-      const double B_t = is_flux ? kr_t * Mn_old : 0.0;
+      const double f = fma(m_old, fma(alpha2, m_old, alpha), -(beta * m_next));
+      const double base = fma(dt, fma(s_own, f, s_src * shfl(f, f_src)), m_old);
+      const double A_t = kf_t * shfl(m_old, src_den);                // F = dt*(kf*M_den*b - kr*M_num), old-time M
+      const double B_t = kr_t * shfl(m_old, src_num);
+      // aSFK: I_a + ca*Etot*I_i/(1 + cf*Etot) = (I_a + (cf*I_a + ca*I_i)*Etot)/(1 + cf*Etot)   (basepdesolver.jl:206-207)
+      const double cr = lane == aSFK ? fma(cf, ws[aSFK], ca * ws[iSFK]) : cr_fixed;
 
       // ---- fixed-point iterations (basepdesolver.jl:197-242) ----
       int it = 0;
-      double Et = Etot_prev;                                        // first pass sees last step's membrane values
-      bool go = true, unconverged = false, nan_exit = false;
-      if (a.o.bc_loop == GAB1_BC_FOR_BREAK && a.o.maxiters <= 0) go = false;
-      while (go) {
-        ++it;
-        const double Mn = shfl(x, src_num);
-        double Md = shfl(x, src_den);
-        if (lane < GAB1) Md = Et;
-        const double qv = (lane < GAB1 ? Iq : fma(cr, Mn, Iq)) / fma(cf, Md, 1.0);
-        const double bnew = lane == aSFK ? fma(ca * Et, qv, Ia) : qv;
-        const double F = is_flux ? fma(A_t, bnew, -B_t) : 0.0;
-        double F0 = shfl(F, fs0), F1 = shfl(F, fs1), F2 = shfl(F, fs2), F3 = shfl(F, fs3);
-        F0 = (neg & 1u) ? -F0 : F0; F1 = (neg & 2u) ? -F1 : F1; F2 = (neg & 4u) ? -F2 : F2; F3 = (neg & 8u) ? -F3 : F3;
-        const double mnew = base + F0 + F1 + F2 + F3;
-        const double xnew = lane < NCY ? bnew : mnew;
-        // convergence: |1 - new/old| <= tol for all 18 tracked values, NaN-aware
-        int cls;
-        const bool tracked = lane < ML + NMB;
-        const bool special = tracked && (is_special(x) || is_special(xnew));
-        if (__any_sync(FULL, special)) {
-          cls = tracked ? classify_exact(x, xnew, tol) : 0;
-        } else {
-          cls = (tracked && !(fabs(x - xnew) <= tol * fabs(x))) ? 1 : 0;
-        }
-        x = tracked ? xnew : 0.0;
-        Et = Etot_new;
-        const bool any_nan = __any_sync(FULL, cls == 2);
-        const bool all_ok = __all_sync(FULL, cls == 0);
-        if (a.o.bc_loop == GAB1_BC_FOR_BREAK) {
-          if (all_ok && !any_nan) go = false;
-          else if (it >= a.o.maxiters) { go = false; unconverged = true; }
-        } else {
-          if (any_nan || all_ok) { go = false; nan_exit = any_nan; }   // `while error > tol`: NaN leaves the loop
-          else if (it >= a.o.maxiters) { go = false; status |= GAB1_ST_ITER_CAP; }
-        }
+      bool unconverged = false, nan_exit = false;
+      if (maxiters > 0 || WHILE) {
+        bool go = true;
+        do {
+          ++it;
+          const double Mn = shfl(x, src_num);
+          const double Md = shfl(x, src_den);
+          const double qv = fast_div(fma(cr, Mn, Iq), fma(cf, Md, 1.0));
+          const double F = fma(A_t, qv, -B_t);
+          const double F0 = shfl(F, fs0), F1 = shfl(F, fs1), F2 = shfl(F, fs2), F3 = shfl(F, fs3);
+          const double mnew = fma(sg0, F0, fma(sg1, F1, fma(sg2, F2, fma(sg3, F3, base))));
+          const double xnew = lane < NCY ? qv : mnew;
+          if constexpr (!WHILE) {
+            // |1 - new/old| <= tol  <=>  |old - new| <= tol*|old|; the strict `<` also rejects old = new = 0 (0/0 = NaN
+            // in the reference) and old = +-Inf, so no special cases remain; NaN operands compare false
+            const bool ok = (fabs(x - xnew) < tol * fabs(x)) || untracked;
+            x = xnew;
+            const bool all_ok = __all_sync(FULL, ok);
+            if (all_ok) go = false;
+            else if (it >= maxiters) { go = false; unconverged = true; }
+          } else {
+            // `while error > tol`: a NaN error leaves the loop, so NaN has to be told apart exactly
+            int cls;
+            const bool special = !untracked && (is_special(x) || is_special(xnew));
+            if (__any_sync(FULL, special)) cls = untracked ? 0 : classify_exact(x, xnew, tol);
+            else cls = (!untracked && !(fabs(x - xnew) <= tol * fabs(x))) ? 1 : 0;
+            x = xnew;
+            const bool any_nan = __any_sync(FULL, cls == 2);
+            const bool all_ok = __all_sync(FULL, cls == 0);
+            if (any_nan || all_ok) { go = false; nan_exit = any_nan; }
+            else if (it >= maxiters) { go = false; status |= GAB1_ST_ITER_CAP; }
+          }
+        } while (go);
+      } else if (lane >= ML) {
+        x = 0.0;   // maxiters = 0: column [2] of the membrane arrays is never written (stays zero)
       }
       bc_total += it;
-      if (it == 0 && lane >= ML) x = 0.0;   // maxiters = 0: column [2] of the membrane arrays is never written (stays zero)
-      Etot_prev = Etot_new;
       // ---- boundary values back to the lane that owns node Nr ----
       if (lane < NCY) ws[16 + lane] = x;
       __syncwarp();
+      if (lane == lane_b) {
 #pragma unroll
-      for (int q = 0; q < NCY; ++q) {
-        const double bq = ws[16 + q];
-#pragma unroll
-        for (int i = 0; i < K; ++i) u[q][i] = (lane == lane_b && i == idx_b) ? bq : w[q][i];
+        for (int q = 0; q < NCY; ++q) u[q][idx_b] = ws[16 + q];
       }
       if (unconverged || nan_exit) {
-        bool all_nan = (lane < ML || lane >= ML + NMB) || isnan(x);
+        bool all_nan = (lane < ML || lane >= LE) || isnan(x);
 #pragma unroll
         for (int i = 0; i < K; ++i)
 #pragma unroll
-          for (int q = 0; q < NCY; ++q) all_nan &= (g.node[i] > Nr) || isnan(u[q][i]);
+          for (int q = 0; q < NCY; ++q) all_nan &= (g.node[i] < 1) || isnan(u[q][i]);
         dead = __all_sync(FULL, all_nan);
       }
       if (track_t) {
@@ -750,7 +771,7 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
     for (int j = 0; j < NMB; ++j) m[j] = shfl(x, ML + j);
     // ---- all-NaN state: only the clock and the snapshot schedule still evolve ----
     for (; step <= Nt; ++step) {
-      const long long per = (a.o.bc_loop == GAB1_BC_FOR_BREAK) ? a.o.maxiters : 1;
+      const long long per = WHILE ? 1 : maxiters;
       if (!track_t) { bc_total += (Nt - step + 1) * per; break; }
       bc_total += per;
       t = t + dt;
@@ -795,28 +816,34 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
 
 // ---------------------------------------------------------------------------------------------------------------
 // Persistent kernel: every warp pulls parameter sets from a queue ordered by descending work.
-template <int K, bool STRICT>
-__global__ void __launch_bounds__(128) solve_kernel(const KernelArgs a) {
+template <int K, int MODE>
+__global__ void __launch_bounds__(128, (MODE == MODE_STRICT || K > 2) ? 1 : 3) solve_kernel(const KernelArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* ws = smem + (size_t)warp * (WS_HDR + 2 * a.P_pad);
   const int Nr = a.o.Nr;
+  ws[lane] = 0.0;
+  __syncwarp();
 
   Grid<K> g;
   {
     const double dr = a.o.dr;
     const double inv_dr2 = 1.0 / (dr * dr);
+    g.G = (Nr + K - 1) / K;
+    const int off = Nr - g.G * K;                      // <= 0
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-      const int n = lane * K + 1 + i;
+      const int n = lane * K + i + 1 + off;
       g.node[i] = n;
-      g.interior[i] = n <= Nr - 1;
-      const double r = n <= Nr ? a.r[n] : 1.0;
-      g.r[i] = r;
+      g.interior[i] = n >= 1 && n <= Nr - 1;
+      const double r = (n >= 1 && n <= Nr) ? a.r[n] : 1.0;
       g.a[i] = __ddiv_rn(1.0, __dmul_rn(r, dr));
       const double aj = (a.o.geometry == GAB1_GEOM_SPHERICAL) ? 1.0 / (r * dr) : 0.0;
-      g.cp[i] = g.interior[i] ? inv_dr2 + aj : 0.0;
-      g.cm[i] = g.interior[i] ? inv_dr2 - aj : 0.0;
+      double cp = inv_dr2 + aj, cm = inv_dr2 - aj, c0 = -2.0 * inv_dr2;
+      if (n == 1) { c0 += cm; cm = 0.0; }             // u[0] = u[1]: the mirror term joins the centre coefficient
+      g.cp[i] = g.interior[i] ? cp : 0.0;
+      g.cm[i] = g.interior[i] ? cm : 0.0;
+      g.c0[i] = g.interior[i] ? c0 : 0.0;
     }
   }
   for (;;) {
@@ -825,7 +852,7 @@ __global__ void __launch_bounds__(128) solve_kernel(const KernelArgs a) {
     item = __shfl_sync(FULL, item, 0);
     if ((long long)item >= a.S) break;
     const long long set = a.order ? (long long)a.order[item] : (long long)item;
-    solve_set<K, STRICT>(a, set, lane, ws, g);
+    solve_set<K, MODE>(a, set, lane, ws, g);
     __syncwarp();
   }
 }
