@@ -196,6 +196,10 @@ void gab1_host_free(void* p);
  * DFMA kernel; the roofline denominator bench.py reports. Negative on failure. */
 double gab1_measure_fp64_tflops(int32_t device, double seconds);
 
+/* Diagnostic: worst relative error of the hardware reciprocal seed and of the kernel's reciprocal (seed + one cubic
+ * step) over 4M log-spaced operands in [lo, hi]. */
+int gab1_debug_recip_error(int32_t device, double lo, double hi, double* seed_err, double* recip_err);
+
 /* Number of launches of this library's kernels since load (for the benchmark's gpu_launches). */
 int64_t gab1_kernel_launches(void);
 

@@ -192,6 +192,8 @@ def load_library():
     lib.gab1_host_free.restype = None
     lib.gab1_measure_fp64_tflops.argtypes = [C.c_int32, C.c_double]
     lib.gab1_measure_fp64_tflops.restype = C.c_double
+    lib.gab1_debug_recip_error.argtypes = [C.c_int32, C.c_double, C.c_double, _dp, _dp]
+    lib.gab1_debug_recip_error.restype = C.c_int
     lib.gab1_kernel_launches.argtypes = []
     lib.gab1_kernel_launches.restype = C.c_int64
     lib.gab1_device_count.argtypes = []

@@ -427,6 +427,21 @@ double gab1_measure_fp64_tflops(int32_t device, double seconds) {
 
 int64_t gab1_kernel_launches(void) { return g_launches.load(); }
 
+int gab1_debug_recip_error(int32_t device, double lo, double hi, double* seed_err, double* recip_err) {
+  CUDA_TRY(cudaSetDevice(device));
+  double* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, 16));
+  CUDA_TRY(cudaMemset(d, 0, 16));
+  gab1::recip_error_kernel<<<64, 256>>>(lo, hi, 1 << 22, d);
+  g_launches.fetch_add(1);
+  double h[2] = {0, 0};
+  CUDA_TRY(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  if (seed_err) *seed_err = h[0];
+  if (recip_err) *recip_err = h[1];
+  return 0;
+}
+
 int gab1_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;

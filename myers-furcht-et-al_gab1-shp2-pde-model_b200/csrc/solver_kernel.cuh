@@ -59,7 +59,29 @@ __device__ __forceinline__ sd operator*(sd a, sd b) { return sd(__dmul_rn(a.v, b
 __device__ __forceinline__ sd operator/(sd a, sd b) { return sd(__ddiv_rn(a.v, b.v)); }
 __device__ __forceinline__ sd operator-(sd a) { return sd(-a.v); }
 
-__device__ __forceinline__ double shfl(double x, int src) { return __shfl_sync(FULL, x, src); }
+// 64-bit shuffles spelled as two 32-bit ones: with the built-in double overload ptxas lands the halves in swapped
+// registers and repairs each shuffle with three XORs (ncu profile r1b: 60 LOP3 per step)
+__device__ __forceinline__ double shfl(double x, int src) {
+  const int lo = __shfl_sync(FULL, __double2loint(x), src), hi = __shfl_sync(FULL, __double2hiint(x), src);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_up1(double x) {
+  const int lo = __shfl_up_sync(FULL, __double2loint(x), 1), hi = __shfl_up_sync(FULL, __double2hiint(x), 1);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_down1(double x) {
+  const int lo = __shfl_down_sync(FULL, __double2loint(x), 1), hi = __shfl_down_sync(FULL, __double2hiint(x), 1);
+  return __hiloint2double(hi, lo);
+}
+// shared memory through a 32-bit shared-window address: one register, no generic-address arithmetic in the time loop
+__device__ __forceinline__ double lds(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts(unsigned addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
 __device__ __forceinline__ bool is_special(double x) {   // zero, Inf or NaN — decided on the bit pattern, off the FP64 pipe
   const unsigned hi = (unsigned)__double2hiint(x) & 0x7fffffffu;
   const unsigned lo = (unsigned)__double2loint(x);
@@ -351,16 +373,14 @@ __device__ int membrane_strict(const KernelArgs& a, const Rates& k, double kp_no
 // MODE 0: fast arithmetic, `for ... break` membrane loop; 1: fast arithmetic, `while error > tol` loop; 2: strict.
 enum { MODE_FAST_FOR = 0, MODE_FAST_WHILE = 1, MODE_STRICT = 2 };
 
-__device__ __forceinline__ double fast_div(double a, double b) {
-  // reciprocal seed + two Newton steps + one residual correction: <= 1 ulp for normal operands, no slow-path branch
+// 1/b for the Robin closures: hardware seed (MUFU.RCP64H, ~2^-20) and one cubic step r*(1 + e + e^2), e = 1 - b*r:
+// relative error ~2^-60 before the final rounding, three dependent FP64 operations, no slow-path branch.
+// (The quotient num*r then carries <= 2 ulp; measured by gab1_debug_recip_error / tests.)
+__device__ __forceinline__ double fast_recip(double b) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-  double e = fma(-b, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-b, r, 1.0);
-  r = fma(r, e, r);
-  const double q = a * r;
-  return fma(fma(-b, q, a), r, q);
+  const double e = fma(-b, r, 1.0);
+  return fma(r, fma(e, e, e), r);
 }
 
 template <int K, int MODE>
@@ -618,6 +638,7 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
     const int iq_idx = lane < NCY ? lane : 10;             // ws[10..15] stay zero
     const bool pulse = a.o.t_prechase >= 0.0;
     const int maxiters = a.o.maxiters;
+    const unsigned ws_s = (unsigned)__cvta_generic_to_shared(ws);
     // x: the value this lane tracks across iterations and steps — boundary value u[Nr+1] of species `lane`
     // (lanes 0..9), membrane species lane-10 (lanes 10..17), Etot (lane 18), zero elsewhere
     double x = (lane == ML + mE) ? CoEGFR : 0.0;
@@ -626,13 +647,26 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
       if (pulse) {                                         // pulsechase_solver.jl:156-158
         if (a.o.t_prechase + dt > t && t >= a.o.t_prechase) { kp_now = 0.0; if (lane == ML + mESmES) alpha = 0.0; }
       }
+      // ---- membrane block prologue: everything that depends only on old-time values.  It is independent of the
+      //      interior update below, so the two instruction streams interleave and hide each other's latency ----
+      const double m_old = x;                                        // lanes >= 10: value at the old time level
+      const double m_next = shfl_down1(m_old);
+      const double f = fma(m_old, fma(alpha2, m_old, alpha), -(beta * m_next));
+      const double base = fma(dt, fma(s_own, f, s_src * shfl(f, f_src)), m_old);
+      // the first iterate of the membrane column is the old-time column, so these two shuffles serve both the
+      // old-time flux coefficients and the first pass of the fixed point
+      const double Md1 = shfl(m_old, src_den), Mn1 = shfl(m_old, src_num);
+      const double A_t = kf_t * Md1;                                 // F = dt*(kf*M_den*b - kr*M_num), old-time M
+      const double B_t = kr_t * Mn1;
+      const double rden1 = fast_recip(fma(cf, Md1, 1.0));            // 1/(1 + cf*M_den) of the first pass
+
       // ---- interior: D*lap + kinetics, explicit Euler, updated in place (basepdesolver.jl:150-180) ----
       {
         double hl[NCY], hr[NCY];
 #pragma unroll
         for (int q = 0; q < NCY; ++q) {
-          hl[q] = __shfl_up_sync(FULL, u[q][K - 1], 1);
-          hr[q] = __shfl_down_sync(FULL, u[q][0], 1);
+          hl[q] = shfl_up1(u[q][K - 1]);
+          hr[q] = shfl_down1(u[q][0]);
         }
         double L[2][NCY];     // Laplacians of the node being updated and of the next one (which still needs old values)
 #pragma unroll
@@ -670,36 +704,27 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
           u[SHP2][i] = fma(Dt_S2, lap[SHP2], S2 - v4 - v7);
           u[PG1S][i] = fma(Dt_G1S2, lap[PG1S], pg1s + v4 - v5);
           u[G2PG1S][i] = fma(Dt_G2G1S2, lap[G2PG1S], g2pg1s + v5 + v7);
+          if (i == idx_i) {
+            // hand the inner-neighbour values u+[Nr-1] to the closure lanes as soon as they exist; the loads that
+            // pick them up sit behind the rest of the interior work
+            if (lane == lane_i) {
+#pragma unroll
+              for (int q = 0; q < NCY; ++q) sts(ws_s + 8 * q, u[q][i]);
+            }
+          }
         }
       }
-      // ---- hand the inner-neighbour values u+[Nr-1] to the closure lanes ----
-      if (lane == lane_i) {
-#pragma unroll
-        for (int q = 0; q < NCY; ++q) ws[q] = u[q][idx_i];
-      }
       __syncwarp();
-      const double Iq = ws[iq_idx];
-
-      // ---- membrane block prologue: everything that depends only on old-time values ----
-      const double m_old = x;                                        // lanes >= 10: value at the old time level
-      const double m_next = __shfl_down_sync(FULL, m_old, 1);
-      const double f = fma(m_old, fma(alpha2, m_old, alpha), -(beta * m_next));
-      const double base = fma(dt, fma(s_own, f, s_src * shfl(f, f_src)), m_old);
-      const double A_t = kf_t * shfl(m_old, src_den);                // F = dt*(kf*M_den*b - kr*M_num), old-time M
-      const double B_t = kr_t * shfl(m_old, src_num);
+      const double Iq = lds(ws_s + 8 * iq_idx);
       // aSFK: I_a + ca*Etot*I_i/(1 + cf*Etot) = (I_a + (cf*I_a + ca*I_i)*Etot)/(1 + cf*Etot)   (basepdesolver.jl:206-207)
-      const double cr = lane == aSFK ? fma(cf, ws[aSFK], ca * ws[iSFK]) : cr_fixed;
+      const double cr = lane == aSFK ? fma(cf, Iq, ca * lds(ws_s + 8 * iSFK)) : cr_fixed;
 
-      // ---- fixed-point iterations (basepdesolver.jl:197-242) ----
+      // ---- fixed-point iterations (basepdesolver.jl:197-242); the first pass is peeled: its reciprocal is ready ----
       int it = 0;
       bool unconverged = false, nan_exit = false;
       if (maxiters > 0 || WHILE) {
-        bool go = true;
-        do {
-          ++it;
-          const double Mn = shfl(x, src_num);
-          const double Md = shfl(x, src_den);
-          const double qv = fast_div(fma(cr, Mn, Iq), fma(cf, Md, 1.0));
+        // everything after the closure value qv of one pass; returns true when another pass is needed
+        auto finish_pass = [&](double qv) -> bool {
           const double F = fma(A_t, qv, -B_t);
           const double F0 = shfl(F, fs0), F1 = shfl(F, fs1), F2 = shfl(F, fs2), F3 = shfl(F, fs3);
           const double mnew = fma(sg0, F0, fma(sg1, F1, fma(sg2, F2, fma(sg3, F3, base))));
@@ -709,9 +734,9 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
             // in the reference) and old = +-Inf, so no special cases remain; NaN operands compare false
             const bool ok = (fabs(x - xnew) < tol * fabs(x)) || untracked;
             x = xnew;
-            const bool all_ok = __all_sync(FULL, ok);
-            if (all_ok) go = false;
-            else if (it >= maxiters) { go = false; unconverged = true; }
+            if (__all_sync(FULL, ok)) return false;
+            if (it >= maxiters) { unconverged = true; return false; }
+            return true;
           } else {
             // `while error > tol`: a NaN error leaves the loop, so NaN has to be told apart exactly
             int cls;
@@ -721,20 +746,29 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
             x = xnew;
             const bool any_nan = __any_sync(FULL, cls == 2);
             const bool all_ok = __all_sync(FULL, cls == 0);
-            if (any_nan || all_ok) { go = false; nan_exit = any_nan; }
-            else if (it >= maxiters) { go = false; status |= GAB1_ST_ITER_CAP; }
+            if (any_nan || all_ok) { nan_exit = any_nan; return false; }
+            if (it >= maxiters) { status |= GAB1_ST_ITER_CAP; return false; }
+            return true;
           }
-        } while (go);
+        };
+        it = 1;
+        bool more = finish_pass(fma(cr, Mn1, Iq) * rden1);
+        while (more) {
+          ++it;
+          const double Mn = shfl(x, src_num);
+          const double Md = shfl(x, src_den);
+          more = finish_pass(fma(cr, Mn, Iq) * fast_recip(fma(cf, Md, 1.0)));
+        }
       } else if (lane >= ML) {
         x = 0.0;   // maxiters = 0: column [2] of the membrane arrays is never written (stays zero)
       }
       bc_total += it;
       // ---- boundary values back to the lane that owns node Nr ----
-      if (lane < NCY) ws[16 + lane] = x;
+      if (lane < NCY) sts(ws_s + 8 * (16 + lane), x);
       __syncwarp();
       if (lane == lane_b) {
 #pragma unroll
-        for (int q = 0; q < NCY; ++q) u[q][idx_b] = ws[16 + q];
+        for (int q = 0; q < NCY; ++q) u[q][idx_b] = lds(ws_s + 8 * (16 + q));
       }
       if (unconverged || nan_exit) {
         bool all_nan = (lane < ML || lane >= LE) || isnan(x);
@@ -817,7 +851,10 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
 // ---------------------------------------------------------------------------------------------------------------
 // Persistent kernel: every warp pulls parameter sets from a queue ordered by descending work.
 template <int K, int MODE>
-__global__ void __launch_bounds__(128, (MODE == MODE_STRICT || K > 2) ? 1 : 3) solve_kernel(const KernelArgs a) {
+#ifndef GAB1_MINB
+#define GAB1_MINB 2
+#endif
+__global__ void __launch_bounds__(128, (MODE == MODE_STRICT || K > 2) ? 1 : GAB1_MINB) solve_kernel(const KernelArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* ws = smem + (size_t)warp * (WS_HDR + 2 * a.P_pad);
@@ -854,6 +891,27 @@ __global__ void __launch_bounds__(128, (MODE == MODE_STRICT || K > 2) ? 1 : 3) s
     const long long set = a.order ? (long long)a.order[item] : (long long)item;
     solve_set<K, MODE>(a, set, lane, ws, g);
     __syncwarp();
+  }
+}
+
+// max relative error of the seed and of fast_recip over n log-spaced operands in [lo, hi] (diagnostic)
+__global__ void recip_error_kernel(double lo, double hi, int n, double* out) {
+  double worst_seed = 0.0, worst = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double b = lo * exp(log(hi / lo) * ((double)i / (double)(n - 1)));
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(b));
+    const double exact = __drcp_rn(b);
+    worst_seed = fmax(worst_seed, fabs(r0 - exact) / exact);
+    worst = fmax(worst, fabs(fast_recip(b) - exact) / exact);
+  }
+  for (int o = 16; o; o >>= 1) {
+    worst_seed = fmax(worst_seed, __shfl_xor_sync(FULL, worst_seed, o));
+    worst = fmax(worst, __shfl_xor_sync(FULL, worst, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax((unsigned long long*)&out[0], (unsigned long long)__double_as_longlong(worst_seed));
+    atomicMax((unsigned long long*)&out[1], (unsigned long long)__double_as_longlong(worst));
   }
 }
 

@@ -238,3 +238,15 @@ def test_whole_ensemble_properties_config2(pkg, gfe, ensemble):
     assert np.abs((good[:, :P] + good[:, P:2 * P]) / Co[0] - 1).max() < 1e-11
     ratio = res.n_bc_iters / res.n_steps
     assert 1.4 < np.median(ratio) < 1.6                                 # 1.51 measured with the oracle
+
+
+def test_reciprocal_accuracy(pkg, gfe):
+    """The Robin closures divide through a hardware reciprocal seed plus one cubic correction; its error must stay at
+    the rounding level over the whole range the denominators 1 + kf*M*dr/D can take."""
+    import ctypes as C
+    lib = pkg.abi.load_library()
+    seed, rec = C.c_double(), C.c_double()
+    assert lib.gab1_debug_recip_error(0, 1e-3, 1e12, C.byref(seed), C.byref(rec)) == 0
+    print(f"seed rel err {seed.value:.3e}, reciprocal rel err {rec.value:.3e}")
+    assert seed.value < 2.0 ** -18
+    assert rec.value < 4 * 2.0 ** -53
