@@ -41,6 +41,8 @@ CFG = dict(dr=0.2, R=10.0, tf=5.0, Nts=100, tol=1e-4, maxiters=20)
 
 def workload(pkg):
     ens = pkg.params.load_parameter_ensemble()
+    if CFG.get("sets"):
+        ens = ens[:CFG["sets"]]
     D = np.ascontiguousarray(ens[:, :7])
     k = np.ascontiguousarray(ens[:, 7:])
     Co = pkg.params.base_Co(CFG["R"])
@@ -303,9 +305,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
+    ap.add_argument("--dr", type=float, default=None, help="experiment: other radial step (not the reported workload)")
+    ap.add_argument("--sets", type=int, default=None, help="experiment: use only the first N rows")
     args = ap.parse_args()
     import __graft_entry__ as g
     g.build()
+    if args.dr is not None:
+        CFG["dr"] = args.dr
+        CONFIG["workload"] += f" [EXPERIMENT dr={args.dr}]"
+    if args.sets is not None:
+        CFG["sets"] = args.sets
+        CONFIG["workload"] += f" [EXPERIMENT first {args.sets} rows]"
     if args.impl == "reference":
         run_reference(args)
     else:

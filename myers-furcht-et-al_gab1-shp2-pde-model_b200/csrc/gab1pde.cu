@@ -101,14 +101,15 @@ int launch(const gab1::KernelArgs& args, int device, cudaStream_t stream) {
   static std::mutex mu;
   static int blocks_per_sm[64] = {0};
   static int sms[64] = {0};
-  const size_t smem = (size_t)4 * (gab1::WS_HDR + 2 * (size_t)args.P_pad) * sizeof(double);
+  constexpr int TPB = 32 * gab1::kWarpsPerCta;
+  const size_t smem = (size_t)gab1::kWarpsPerCta * (gab1::WS_HDR + 2 * (size_t)args.P_pad) * sizeof(double);
   auto kern = gab1::solve_kernel<K, MODE>;
   {
     std::lock_guard<std::mutex> lk(mu);
     if (device < 64 && blocks_per_sm[device] == 0) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       int n = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 128, smem));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, TPB, smem));
       if (n < 1) return fail(-5, "kernel does not fit on an SM (K=%d, smem=%zu)", K, smem);
       blocks_per_sm[device] = n;
       CUDA_TRY(cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device));
@@ -117,15 +118,15 @@ int launch(const gab1::KernelArgs& args, int device, cudaStream_t stream) {
   int nb = 0, nsm = 0;
   if (device < 64) { nb = blocks_per_sm[device]; nsm = sms[device]; }
   if (nb == 0) {
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 128, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, TPB, smem));
     CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
   }
   // persistent grid: a multiple of the SM count; never more warps than sets
   long long grid = (long long)nsm * nb;
-  const long long need = (args.S + 3) / 4;
+  const long long need = (args.S + gab1::kWarpsPerCta - 1) / gab1::kWarpsPerCta;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, 128, smem, stream>>>(args);
+  kern<<<(unsigned)grid, TPB, smem, stream>>>(args);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -170,7 +171,11 @@ int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long 
     CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp, bytes, w.keys_in, w.keys_out, w.vals_in, w.vals_out,
                                                        (int)S, 0, 32, stream));
   }
-  const int mode = o->arith == 1 ? gab1::MODE_STRICT : (o->bc_loop == GAB1_BC_WHILE ? gab1::MODE_FAST_WHILE : gab1::MODE_FAST_FOR);
+  // `maxiters = 0` with the for-loop form never runs the membrane block (degenerate but legal): the strict kernel
+  // reproduces it exactly, the fast kernels assume at least one pass
+  const bool degenerate = o->bc_loop == GAB1_BC_FOR_BREAK && o->maxiters == 0;
+  const int mode = (o->arith == 1 || degenerate) ? gab1::MODE_STRICT
+                   : (o->bc_loop == GAB1_BC_WHILE ? gab1::MODE_FAST_WHILE : gab1::MODE_FAST_FOR);
 #define GAB1_LAUNCH(KK)                                                                          \
   case KK:                                                                                       \
     return mode == gab1::MODE_STRICT       ? launch<KK, gab1::MODE_STRICT>(a, device, stream)     \

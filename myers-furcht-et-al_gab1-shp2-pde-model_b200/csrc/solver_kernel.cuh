@@ -643,10 +643,30 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
     // (lanes 0..9), membrane species lane-10 (lanes 10..17), Etot (lane 18), zero elsewhere
     double x = (lane == ML + mE) ? CoEGFR : 0.0;
 
-    for (; step <= Nt && !dead; ++step) {
-      if (pulse) {                                         // pulsechase_solver.jl:156-158
-        if (a.o.t_prechase + dt > t && t >= a.o.t_prechase) { kp_now = 0.0; if (lane == ML + mESmES) alpha = 0.0; }
+    // ---- time loop.  Every rare event (snapshot due, pulse-chase switch, last step, dead state) hides behind one integer
+    //      countdown, so the common step carries a single predictable branch besides the fixed-point loop.  `plan`
+    //      returns a conservative count of steps that cannot contain an event; the exact floating-point tests of the
+    //      reference (t >= t_save, t_prechase + dt > t >= t_prechase) are then applied step by step around the event.
+    bool pulse_pending = pulse;
+    if (pulse_pending && a.o.t_prechase + dt > t && t >= a.o.t_prechase) {      // pulsechase_solver.jl:156-158 at step 1
+      kp_now = 0.0; if (lane == ML + mESmES) alpha = 0.0; pulse_pending = false;
+    }
+    auto plan = [&]() -> int {
+      long long n = Nt - step + 1;
+      auto bound = [&](double t_event) {
+        const double q = floor((t_event - t) / dt) - 1.0;                      // accumulated t is within ulps of step*dt
+        if (!(q >= 1.0)) n = 1;
+        else if (q < (double)n) n = (long long)q;
+      };
+      if (track_t) {
+        if (a.o.save_rule == GAB1_SAVE_T_GE_TSAVE) bound(t_save); else n = 1;
       }
+      if (pulse_pending) bound(a.o.t_prechase);
+      return (int)(n > 1000000000LL ? 1000000000LL : n);
+    };
+    int countdown = plan();
+    if (Nt >= 1)
+    for (;;) {
       // ---- membrane block prologue: everything that depends only on old-time values.  It is independent of the
       //      interior update below, so the two instruction streams interleave and hide each other's latency ----
       const double m_old = x;                                        // lanes >= 10: value at the old time level
@@ -720,14 +740,14 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
       const double cr = lane == aSFK ? fma(cf, Iq, ca * lds(ws_s + 8 * iSFK)) : cr_fixed;
 
       // ---- fixed-point iterations (basepdesolver.jl:197-242); the first pass is peeled: its reciprocal is ready ----
-      int it = 0;
+      int it = 1;               // the host routes `maxiters = 0` to the strict kernel: at least one pass runs here
       bool unconverged = false, nan_exit = false;
-      if (maxiters > 0 || WHILE) {
+      {
         // everything after the closure value qv of one pass; returns true when another pass is needed
         auto finish_pass = [&](double qv) -> bool {
           const double F = fma(A_t, qv, -B_t);
           const double F0 = shfl(F, fs0), F1 = shfl(F, fs1), F2 = shfl(F, fs2), F3 = shfl(F, fs3);
-          const double mnew = fma(sg0, F0, fma(sg1, F1, fma(sg2, F2, fma(sg3, F3, base))));
+          const double mnew = fma(sg0, F0, sg1 * F1) + fma(sg2, F2, fma(sg3, F3, base));     // depth 3 instead of 4
           const double xnew = lane < NCY ? qv : mnew;
           if constexpr (!WHILE) {
             // |1 - new/old| <= tol  <=>  |old - new| <= tol*|old|; the strict `<` also rejects old = new = 0 (0/0 = NaN
@@ -751,7 +771,6 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
             return true;
           }
         };
-        it = 1;
         bool more = finish_pass(fma(cr, Mn1, Iq) * rden1);
         while (more) {
           ++it;
@@ -759,8 +778,6 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
           const double Md = shfl(x, src_den);
           more = finish_pass(fma(cr, Mn, Iq) * fast_recip(fma(cf, Md, 1.0)));
         }
-      } else if (lane >= ML) {
-        x = 0.0;   // maxiters = 0: column [2] of the membrane arrays is never written (stays zero)
       }
       bc_total += it;
       // ---- boundary values back to the lane that owns node Nr ----
@@ -777,9 +794,12 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
 #pragma unroll
           for (int q = 0; q < NCY; ++q) all_nan &= (g.node[i] < 1) || isnan(u[q][i]);
         dead = __all_sync(FULL, all_nan);
+        if (dead) countdown = 1;
       }
+      t = t + dt;                                                   // basepdesolver.jl:265
+      if (--countdown > 0) { ++step; continue; }
+      // ---- rare path: exact event tests for the step just taken ----
       if (track_t) {
-        t = t + dt;
         const bool save = a.o.save_rule == GAB1_SAVE_T_GE_TSAVE ? (t >= t_save) : (fmod((double)step, modulus_step) == 0.0);
         if (save) {
           if (nts >= Cn) status |= GAB1_ST_OVERFLOW;
@@ -799,6 +819,13 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
           if (a.o.save_rule == GAB1_SAVE_T_GE_TSAVE) t_save = t_save + a.o.dt_save;
         }
       }
+      if (pulse_pending) {                                          // the test the next step would make at its start
+        if (a.o.t_prechase + dt > t && t >= a.o.t_prechase) { kp_now = 0.0; if (lane == ML + mESmES) alpha = 0.0; pulse_pending = false; }
+        else if (t >= a.o.t_prechase + dt) pulse_pending = false;   // the window was stepped over: the reference never switches
+      }
+      ++step;
+      if (dead || step > Nt) break;
+      countdown = plan();
     }
     double m[NMB];
 #pragma unroll
@@ -850,11 +877,18 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
 
 // ---------------------------------------------------------------------------------------------------------------
 // Persistent kernel: every warp pulls parameter sets from a queue ordered by descending work.
-template <int K, int MODE>
+// Launch shape of the product kernels (K <= 2, fast arithmetic): GAB1_WARPS warps per CTA, at least GAB1_MINB CTAs per
+// SM (which caps registers per thread).  Chosen from measurements on B200, see DESIGN.md.
+#ifndef GAB1_WARPS
+#define GAB1_WARPS 4
+#endif
 #ifndef GAB1_MINB
 #define GAB1_MINB 2
 #endif
-__global__ void __launch_bounds__(128, (MODE == MODE_STRICT || K > 2) ? 1 : GAB1_MINB) solve_kernel(const KernelArgs a) {
+constexpr int kWarpsPerCta = GAB1_WARPS;
+template <int K, int MODE>
+__global__ void __launch_bounds__(32 * GAB1_WARPS, (MODE == MODE_STRICT || K > 2) ? 1 : GAB1_MINB)
+solve_kernel(const KernelArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* ws = smem + (size_t)warp * (WS_HDR + 2 * a.P_pad);
