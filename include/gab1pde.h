@@ -188,7 +188,12 @@ int gab1_solve_batch_device(const gab1_opts* o, int32_t device, void* stream, in
                             int64_t* n_steps, int64_t* n_bc_iters,
                             void* workspace);
 
-/* Pinned host allocations for callers that want copies overlapped with compute. */
+/* The sharding gab1_solve_batch applies: bounds[g]..bounds[g+1] is the contiguous range of set indices device g
+ * solves; ranges are balanced by total step count ceil(tf/dt).  Pure host code; bounds has n_shards+1 entries. */
+int gab1_plan_shards(int64_t S, const double* dt, double tf, int32_t n_shards, int64_t* bounds);
+
+/* Pinned, device-mapped host allocations.  When `out` of gab1_solve_batch lives in such memory the kernels write the
+ * snapshots straight into it while the time loop runs (no device copy of the output, no D2H phase). */
 void* gab1_host_alloc(size_t bytes);
 void gab1_host_free(void* p);
 

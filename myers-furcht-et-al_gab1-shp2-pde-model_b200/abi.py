@@ -186,6 +186,8 @@ def load_library():
     lib.gab1_opts_init.restype = None
     lib.gab1_default_dt.argtypes = [C.c_int64, _dp, _dp, C.c_double, _dp]
     lib.gab1_default_dt.restype = C.c_int
+    lib.gab1_plan_shards.argtypes = [C.c_int64, _dp, C.c_double, C.c_int32, _i64p]
+    lib.gab1_plan_shards.restype = C.c_int
     lib.gab1_host_alloc.argtypes = [C.c_size_t]
     lib.gab1_host_alloc.restype = C.c_void_p
     lib.gab1_host_free.argtypes = [C.c_void_p]
@@ -223,3 +225,28 @@ class CudaBackend:
         if rc != 0:
             raise Gab1Error(f"gab1_solve_batch failed ({rc}): {lib.gab1_last_error().decode(errors='replace')}")
         return out, status, n_saved, n_steps, n_bc
+
+
+def plan_shards(dt, tf: float, n_shards: int) -> np.ndarray:
+    """bounds[g]..bounds[g+1]: the contiguous, step-count-balanced range of sets that device/rank g solves."""
+    lib = load_library()
+    dt = np.ascontiguousarray(dt, dtype=np.float64)
+    bounds = np.zeros(n_shards + 1, dtype=np.int64)
+    if lib.gab1_plan_shards(dt.shape[0], _ptr(dt, _dp), float(tf), n_shards, _ptr(bounds, _i64p)) != 0:
+        raise Gab1Error(lib.gab1_last_error().decode())
+    return bounds
+
+
+def pinned_empty(n: int, dtype=np.float64):
+    """numpy view of pinned, device-mapped host memory from gab1_host_alloc (caller frees with pinned_free)."""
+    lib = load_library()
+    nbytes = int(n) * np.dtype(dtype).itemsize
+    p = lib.gab1_host_alloc(nbytes)
+    if not p:
+        raise MemoryError(lib.gab1_last_error().decode())
+    a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,)).view(dtype)
+    return p, a
+
+
+def pinned_free(p) -> None:
+    load_library().gab1_host_free(p)

@@ -161,7 +161,6 @@ int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long 
   a.P_pad = (o->Nr + 1 + 3) & ~3;
 
   CUDA_TRY(cudaMemsetAsync(w.counter, 0, sizeof(unsigned), stream));
-  CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)a.out_stride * (size_t)S, stream));
   {
     const int tb = 256;
     work_keys_kernel<<<(unsigned)((S + tb - 1) / tb), tb, 0, stream>>>(S, dt, o->tf, w.keys_in, w.vals_in);
@@ -304,7 +303,17 @@ static int run_shard(const gab1_opts* o, int device, int64_t lo, int64_t hi, con
     CUDA_TRY(cudaMalloc(&dk, (size_t)S * GAB1_N_K * sizeof(double)));
     CUDA_TRY(cudaMalloc(&ddt, (size_t)S * sizeof(double)));
     CUDA_TRY(cudaMalloc(&dr_, P * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&dout, (size_t)S * nout * sizeof(double)));
+    // A pinned (mapped) caller buffer is written by the kernel directly: snapshot stores stream over PCIe while the
+    // time loop runs, so there is no device copy of the 0.5 MB/set output and no D2H phase.  Pageable buffers are staged.
+    double* out_direct = nullptr;
+    {
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, out + lo * nout) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+        out_direct = (double*)attr.devicePointer;
+      else
+        (void)cudaGetLastError();
+    }
+    if (!out_direct) CUDA_TRY(cudaMalloc(&dout, (size_t)S * nout * sizeof(double)));
     CUDA_TRY(cudaMalloc(&dstatus, (size_t)S * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(&dsaved, (size_t)S * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(&dsteps, (size_t)S * sizeof(int64_t)));
@@ -315,10 +324,11 @@ static int run_shard(const gab1_opts* o, int device, int64_t lo, int64_t hi, con
     CUDA_TRY(cudaMemcpyAsync(dk, k + lo * GAB1_N_K, (size_t)S * GAB1_N_K * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(ddt, dt + lo, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(dr_, r, P * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (int e = solve_device(o, device, st, S, dCo, Co_stride, dD, dk, ddt, dr_, dout, dstatus, dsaved,
-                             (long long*)dsteps, (long long*)dbc, ws))
+    if (int e = solve_device(o, device, st, S, dCo, Co_stride, dD, dk, ddt, dr_, out_direct ? out_direct : dout, dstatus,
+                             dsaved, (long long*)dsteps, (long long*)dbc, ws))
       return e;
-    CUDA_TRY(cudaMemcpyAsync(out + lo * nout, dout, (size_t)S * nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (!out_direct)
+      CUDA_TRY(cudaMemcpyAsync(out + lo * nout, dout, (size_t)S * nout * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (status) CUDA_TRY(cudaMemcpyAsync(status + lo, dstatus, (size_t)S * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (n_saved) CUDA_TRY(cudaMemcpyAsync(n_saved + lo, dsaved, (size_t)S * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (n_steps) CUDA_TRY(cudaMemcpyAsync(n_steps + lo, dsteps, (size_t)S * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -349,25 +359,8 @@ int gab1_solve_batch(const gab1_opts* o, int64_t S, const double* Co, int64_t Co
   std::vector<int> devs(nd);
   for (int i = 0; i < nd; ++i) devs[i] = o->device_ids ? o->device_ids[i] : i;
 
-  // contiguous shards with equal total step count, so that the gather is one copy per device
   std::vector<int64_t> bounds(nd + 1, 0);
-  {
-    std::vector<double> work((size_t)S);
-    double total = 0.0;
-    for (int64_t i = 0; i < S; ++i) {
-      const double n = ceil(o->tf / dt[i]);
-      work[i] = (n > 0.0 && n < 4.0e9) ? n : 1.0;
-      total += work[i];
-    }
-    double acc = 0.0;
-    int g = 1;
-    for (int64_t i = 0; i < S && g < nd; ++i) {
-      acc += work[i];
-      if (acc >= total * g / nd) bounds[g++] = i + 1;
-    }
-    for (; g < nd; ++g) bounds[g] = S;
-    bounds[nd] = S;
-  }
+  gab1_plan_shards(S, dt, o->tf, nd, bounds.data());
   if (nd == 1) return run_shard(o, devs[0], 0, S, Co, Co_stride, D, k, dt, r, out, status, n_saved, n_steps, n_bc_iters);
 
   std::vector<int> rcs(nd, 0);
@@ -385,9 +378,31 @@ int gab1_solve_batch(const gab1_opts* o, int64_t S, const double* Co, int64_t Co
   return 0;
 }
 
+// contiguous shards with (nearly) equal total step count, so that each device's gather is one copy
+int gab1_plan_shards(int64_t S, const double* dt, double tf, int32_t n_shards, int64_t* bounds) {
+  if (S < 0 || n_shards < 1 || !dt || !bounds) return fail(-2, "bad arguments to gab1_plan_shards");
+  std::vector<double> work((size_t)S);
+  double total = 0.0;
+  for (int64_t i = 0; i < S; ++i) {
+    const double n = ceil(tf / dt[i]);
+    work[i] = (n > 0.0 && n < 4.0e9) ? n : 1.0;
+    total += work[i];
+  }
+  bounds[0] = 0;
+  double acc = 0.0;
+  int g = 1;
+  for (int64_t i = 0; i < S && g < n_shards; ++i) {
+    acc += work[i];
+    while (g < n_shards && acc >= total * g / n_shards) bounds[g++] = i + 1;
+  }
+  for (; g < n_shards; ++g) bounds[g] = S;
+  bounds[n_shards] = S;
+  return 0;
+}
+
 void* gab1_host_alloc(size_t bytes) {
   void* p = nullptr;
-  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
     fail(-8, "cudaHostAlloc(%zu) failed", bytes);
     return nullptr;
   }

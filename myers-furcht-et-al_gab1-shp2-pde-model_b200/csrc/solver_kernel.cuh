@@ -410,12 +410,13 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
   const bool track_t = (a.o.out_mode == GAB1_OUT_FULL || a.o.out_mode == GAB1_OUT_PCT_BOUND);
   const long long nout = a.out_stride;
 
-  // the caller's block is already zero (host clears `out`): unsaved columns stay 0 like the reference's zeros(...)
-  (void)nout;
+  // the kernel writes every element of the set's block itself (snapshot columns that never become due are zero-filled
+  // at the end, like the reference's zeros(...) arrays), so `out` needs no clearing and may be mapped host memory
 
   // Nt = Int64(ceil(tf/dt)) (basepdesolver.jl:72)
   const double nt_f = ceil(__ddiv_rn(a.o.tf, dt));
   if (!(nt_f >= 0.0 && nt_f < 9.0e18)) {
+    for (long long i = lane; i < nout; i += 32) oset[i] = 0.0;
     if (lane == 0) {
       if (a.status) a.status[set] = GAB1_ST_THROW;
       if (a.n_saved) a.n_saved[set] = 0;
@@ -451,10 +452,10 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
     for (int mi = 0; mi < 12; ++mi) {
       if (!((mask >> mi) & 1u)) continue;
       const double v0 = mi == GAB1_M_iSFK ? CoSFK : mi == GAB1_M_GRB2 ? CoG2 : mi == GAB1_M_SHP2 ? CoS2 : mi == GAB1_M_GAB1 ? CoG1 : 0.0;
-      if (v0 != 0.0) for (int n = lane; n < P; n += 32) oset[off + n] = v0;
+      for (int n = lane; n < P; n += 32) oset[off + n] = v0;
       off += (long long)P * Cn;
     }
-    if (lane == 0) oset[off + (long long)GAB1_V_mE * Cn] = CoEGFR;
+    if (lane < GAB1_N_VECTORS) oset[off + (long long)lane * Cn] = lane == GAB1_V_mE ? CoEGFR : 0.0;
   }
 
   double t = 0.0, t_save = a.o.dt_save;
@@ -866,7 +867,19 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
     if (isnan(pct)) status |= GAB1_ST_NAN;
     if (lane == 0) oset[0] = pct;
   }
-  if (track_t && nts < Cn) status |= GAB1_ST_SHORT;
+  if (track_t && nts < Cn) {
+    status |= GAB1_ST_SHORT;
+    if (a.o.out_mode == GAB1_OUT_FULL) {           // columns nts..Nts were never due: they stay zero in the reference
+      long long off = 0;
+      for (int mi = 0; mi < 12; ++mi) {
+        if (!((a.o.matrix_mask >> mi) & 1u)) continue;
+        for (long long i = (long long)nts * P + lane; i < (long long)Cn * P; i += 32) oset[off + i] = 0.0;
+        off += (long long)P * Cn;
+      }
+      for (int v = 0; v < GAB1_N_VECTORS; ++v)
+        for (int c = nts + lane; c < Cn; c += 32) oset[off + (long long)v * Cn + c] = 0.0;
+    }
+  }
   if (lane == 0) {
     if (a.status) a.status[set] = (int)status;
     if (a.n_saved) a.n_saved[set] = track_t ? nts : 0;

@@ -250,3 +250,34 @@ def test_reciprocal_accuracy(pkg, gfe):
     print(f"seed rel err {seed.value:.3e}, reciprocal rel err {rec.value:.3e}")
     assert seed.value < 2.0 ** -18
     assert rec.value < 4 * 2.0 ** -53
+
+
+def test_pinned_output_is_written_in_place(pkg, gfe, ensemble):
+    """`out` in pinned, device-mapped host memory: the kernels store the snapshots straight into it (no device copy,
+    no D2H phase).  Must equal the staged (pageable) path bit for bit, including never-due columns (zero-filled) and
+    a set with an unusable dt (whole block zero); the buffer is pre-filled with garbage to prove every element is written."""
+    import ctypes as C
+    lib = pkg.abi.load_library()
+    Co = pkg.params.base_Co()
+    D, k = np.ascontiguousarray(ensemble[:6, :7]), np.ascontiguousarray(ensemble[:6, 7:])
+    dt = pkg.params.default_dt(D, k, 0.4)
+    dt[2] = np.nan              # THROW
+    dt[4] = 0.03                # so coarse that most snapshot columns are never due (SHORT)
+    o = pkg.abi.make_opts(dr=0.4, tf=0.2, Nts=8, tol=1e-4, maxiters=20)
+    r = pkg.params.julia_range(0.4, 10.0)
+    rc, staged, st_s, *_ = pkg.abi.call_solve(lib.gab1_solve_batch, o, Co, D, k, dt, r)
+    assert rc == 0 and (st_s[4] & pkg.abi.ST_SHORT) and (st_s[2] & pkg.abi.ST_THROW)
+    n = pkg.abi.out_doubles_per_set(o)
+    p, pinned = pkg.abi.pinned_empty(6 * n)
+    try:
+        pinned[:] = -12345.678
+        dp, ip, lp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+        status = np.zeros(6, np.int32)
+        rc = lib.gab1_solve_batch(C.byref(o), 6, Co.ctypes.data_as(dp), 0, D.ctypes.data_as(dp), k.ctypes.data_as(dp),
+                                  dt.ctypes.data_as(dp), r.ctypes.data_as(dp), pinned.ctypes.data_as(dp),
+                                  status.ctypes.data_as(ip), None, None, None)
+        assert rc == 0, lib.gab1_last_error()
+        assert_bits(pinned.reshape(6, n), staged, "pinned vs staged")
+        np.testing.assert_array_equal(status, st_s)
+    finally:
+        pkg.abi.pinned_free(p)

@@ -1,0 +1,84 @@
+"""Host-side logic of the N > 1 path, on CPU: the shard plan of gab1_solve_batch, and a world_size-2 gloo run in which
+each rank solves its shard (with the oracle standing in for the device) and the gathered result equals the single-rank one."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_plan_is_contiguous_balanced_and_complete(pkg, ensemble):
+    import __graft_entry__ as g
+    g.build()
+    dt = pkg.params.default_dt(ensemble[:, :7], ensemble[:, 7:], 0.2)
+    nt = np.ceil(5.0 / dt)
+    for n in (1, 2, 3, 4, 8):
+        b = pkg.abi.plan_shards(dt, 5.0, n)
+        assert b[0] == 0 and b[-1] == len(dt) and np.all(np.diff(b) > 0)
+        loads = np.array([nt[b[i]:b[i + 1]].sum() for i in range(n)])
+        assert loads.max() / loads.mean() < 1.002            # within one set's work of perfect balance
+    # ragged: one huge set dominates; more shards than sets; empty input
+    dt2 = np.array([1e-6, 1e-3, 1e-3, 1e-3])
+    b = pkg.abi.plan_shards(dt2, 1.0, 2)
+    assert list(b) == [0, 1, 4]
+    assert list(pkg.abi.plan_shards(np.array([1e-3, 1e-3]), 1.0, 4))[-1] == 2
+    assert list(pkg.abi.plan_shards(np.zeros(0), 1.0, 2)) == [0, 0, 0]
+    # unusable dt counts as one unit of work instead of poisoning the plan
+    b = pkg.abi.plan_shards(np.array([np.nan, 0.0, 1e-3, 1e-3]), 1.0, 2)
+    assert b[0] == 0 and b[-1] == 4 and np.all(np.diff(b) >= 0)
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, str(ROOT))
+    import importlib
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg = importlib.import_module("myers-furcht-et-al_gab1-shp2-pde-model_b200")
+    from oracle import oracle
+    ens = pkg.params.load_parameter_ensemble()[:12]
+    Co = pkg.params.base_Co()
+    dt = pkg.params.default_dt(ens[:, :7], ens[:, 7:], 0.4)
+    dt[3] *= 0.25                                          # ragged work: the plan must move the boundary
+    b = pkg.abi.plan_shards(dt, 0.2, world)
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    fe = oracle.frontend(1)
+    res = fe.sapdesolver_batch(Co, ens[lo:hi, :7], ens[lo:hi, 7:], dr=0.4, tf=0.2, dt=dt[lo:hi], out_mode=pkg.abi.OUT_SIX)
+    mine = torch.zeros(12, 6, dtype=torch.float64)
+    mine[lo:hi] = torch.from_numpy(res.out)
+    dist.all_reduce(mine)                                  # disjoint shards: the sum is the gather
+    t = torch.tensor([0.1 * (rank + 1)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)               # the max-over-ranks timing bench.py reports
+    if rank == 0:
+        q.put((mine.numpy(), float(t.item()), [int(x) for x in b]))
+    dist.destroy_process_group()
+
+
+def test_two_ranks_gloo_shards_gather_to_single_rank_result(pkg):
+    import torch.multiprocessing as mp
+    from oracle import oracle
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered, tmax, bounds = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ens = pkg.params.load_parameter_ensemble()[:12]
+    dt = pkg.params.default_dt(ens[:, :7], ens[:, 7:], 0.4)
+    dt[3] *= 0.25
+    ref = oracle.frontend(1).sapdesolver_batch(pkg.params.base_Co(), ens[:, :7], ens[:, 7:], dr=0.4, tf=0.2, dt=dt,
+                                                out_mode=pkg.abi.OUT_SIX)
+    np.testing.assert_array_equal(gathered, ref.out)
+    assert tmax == pytest.approx(0.2)
+    assert bounds[0] == 0 and bounds[2] == 12 and bounds[1] < 6     # the heavy set pulls the boundary left
