@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -14,13 +15,15 @@
 #include <vector>
 
 #include "gab1pde.h"
-#include "solver_kernel.cuh"
+#include "launch.h"
 
 namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+}  // namespace
 
+namespace gab1 {
 int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -28,11 +31,15 @@ int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
-#define CUDA_TRY(expr)                                                                                   \
-  do {                                                                                                   \
-    cudaError_t e_ = (expr);                                                                             \
-    if (e_ != cudaSuccess) return fail(-100 - (int)e_, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
-  } while (0)
+void count_launch() { g_launches.fetch_add(1); }
+}  // namespace gab1
+
+#ifndef GAB1_PAIRS_DEFAULT
+#define GAB1_PAIRS_DEFAULT false
+#endif
+
+namespace {
+using gab1::fail;
 
 int popcount12(uint32_t m) { return __builtin_popcount(m & GAB1_MASK_ALL_MATRICES); }
 
@@ -56,10 +63,28 @@ int pick_K(int Nr) {
     if (Nr <= 32 * K) return K;
   return 0;
 }
+// nodes per lane for the two-sets-per-warp kernels: nodes 1..Nr over 16 lanes (0: grid too large for a half warp)
+int pick_pair_K(int Nr) {
+  for (int K : {1, 2, 4})
+    if (Nr <= 16 * K) return K;
+  return 0;
+}
+// GAB1_KERNEL=pair / single selects the kernel family for grids of up to 64 nodes (A/B measurements)
+bool pairs_enabled() {
+  const char* e = getenv("GAB1_KERNEL");
+  if (e && strcmp(e, "single") == 0) return false;
+  if (e && strcmp(e, "pair") == 0) return true;
+  return GAB1_PAIRS_DEFAULT;
+}
 
 // ---- descending-work ordering: key = number of time steps, largest first -------------------------------------
-__global__ void work_keys_kernel(long long S, const double* dt, double tf, unsigned* keys, int* vals) {
+// Thread 0 also sets the guard word the pair kernels check: their spherical stencil drops the zero-flux mirror term of
+// node 1, which is exact only when 1 - dr/r[1] == 0, i.e. on the reference's own grid r = collect(0:dr:R).  For any
+// other r the pair launch returns at once and the general kernel enqueued behind it does the work.
+__global__ void work_keys_kernel(long long S, const double* dt, double tf, unsigned* keys, int* vals, const double* r,
+                                 double dr, int spherical, int* guard) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i == 0) *guard = (spherical && 1.0 - dr / r[1] != 0.0) ? 1 : 0;
   if (i >= S) return;
   const double n = ceil(tf / dt[i]);
   keys[i] = (n >= 0.0 && n < 4.0e9) ? (unsigned)n : 0u;   // unusable dt: no work, goes last
@@ -86,7 +111,7 @@ size_t cub_bytes_for(long long S) {
 size_t carve(Workspace& w, void* base, long long S) {
   size_t off = 0;
   auto take = [&](size_t bytes) { void* p = base ? (char*)base + off : nullptr; off += align_up(bytes, 256); return p; };
-  w.counter = (unsigned*)take(256);
+  w.counter = (unsigned*)take(256);     // [0] queue head, [1] guard word
   w.keys_in = (unsigned*)take(sizeof(unsigned) * (size_t)S);
   w.keys_out = (unsigned*)take(sizeof(unsigned) * (size_t)S);
   w.vals_in = (int*)take(sizeof(int) * (size_t)S);
@@ -94,42 +119,6 @@ size_t carve(Workspace& w, void* base, long long S) {
   w.cub_bytes = cub_bytes_for(S);
   w.cub_tmp = take(w.cub_bytes);
   return off;
-}
-
-template <int K, int MODE>
-int launch(const gab1::KernelArgs& args, int device, cudaStream_t stream) {
-  static std::mutex mu;
-  static int blocks_per_sm[64] = {0};
-  static int sms[64] = {0};
-  constexpr int TPB = 32 * gab1::kWarpsPerCta;
-  const size_t smem = (size_t)gab1::kWarpsPerCta * (gab1::WS_HDR + 2 * (size_t)args.P_pad) * sizeof(double);
-  auto kern = gab1::solve_kernel<K, MODE>;
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    if (device < 64 && blocks_per_sm[device] == 0) {
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      int n = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, TPB, smem));
-      if (n < 1) return fail(-5, "kernel does not fit on an SM (K=%d, smem=%zu)", K, smem);
-      blocks_per_sm[device] = n;
-      CUDA_TRY(cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device));
-    }
-  }
-  int nb = 0, nsm = 0;
-  if (device < 64) { nb = blocks_per_sm[device]; nsm = sms[device]; }
-  if (nb == 0) {
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, TPB, smem));
-    CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
-  }
-  // persistent grid: a multiple of the SM count; never more warps than sets
-  long long grid = (long long)nsm * nb;
-  const long long need = (args.S + gab1::kWarpsPerCta - 1) / gab1::kWarpsPerCta;
-  if (grid > need) grid = need;
-  if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, TPB, smem, stream>>>(args);
-  g_launches.fetch_add(1);
-  CUDA_TRY(cudaGetLastError());
-  return 0;
 }
 
 int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long S, const double* Co, long long Co_stride,
@@ -163,7 +152,8 @@ int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long 
   CUDA_TRY(cudaMemsetAsync(w.counter, 0, sizeof(unsigned), stream));
   {
     const int tb = 256;
-    work_keys_kernel<<<(unsigned)((S + tb - 1) / tb), tb, 0, stream>>>(S, dt, o->tf, w.keys_in, w.vals_in);
+    work_keys_kernel<<<(unsigned)((S + tb - 1) / tb), tb, 0, stream>>>(S, dt, o->tf, w.keys_in, w.vals_in, r, o->dr,
+                                                                       o->geometry == GAB1_GEOM_SPHERICAL, (int*)(w.counter + 1));
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     size_t bytes = w.cub_bytes;
@@ -175,19 +165,16 @@ int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long 
   const bool degenerate = o->bc_loop == GAB1_BC_FOR_BREAK && o->maxiters == 0;
   const int mode = (o->arith == 1 || degenerate) ? gab1::MODE_STRICT
                    : (o->bc_loop == GAB1_BC_WHILE ? gab1::MODE_FAST_WHILE : gab1::MODE_FAST_FOR);
-#define GAB1_LAUNCH(KK)                                                                          \
-  case KK:                                                                                       \
-    return mode == gab1::MODE_STRICT       ? launch<KK, gab1::MODE_STRICT>(a, device, stream)     \
-           : mode == gab1::MODE_FAST_WHILE ? launch<KK, gab1::MODE_FAST_WHILE>(a, device, stream) \
-                                           : launch<KK, gab1::MODE_FAST_FOR>(a, device, stream);
-  switch (K) {
-    GAB1_LAUNCH(1)
-    GAB1_LAUNCH(2)
-    GAB1_LAUNCH(4)
-    GAB1_LAUNCH(8)
+  // ---- grids that fit a half warp: two sets per warp (pair_kernel.cuh) ----
+  const int KP = (mode != gab1::MODE_STRICT && pairs_enabled()) ? pick_pair_K(o->Nr) : 0;
+  if (KP) {
+    const bool mirror = o->geometry != GAB1_GEOM_SPHERICAL;
+    if (!mirror) { a.guard = (const int*)(w.counter + 1); a.guard_expect = 0; }
+    const int rc = gab1::launch_pair_kernel(KP, mode, mirror, a, device, stream);
+    if (rc || mirror) return rc;
+    a.guard_expect = 1;          // the general kernel below runs only if the pair kernel declined the grid
   }
-#undef GAB1_LAUNCH
-  return fail(-6, "no kernel for K=%d", K);
+  return gab1::launch_single_kernel(K, mode, a, device, stream);
 }
 
 // ---- FP64 peak: register-resident DFMA chains ------------------------------------------------------------------
@@ -452,8 +439,7 @@ int gab1_debug_recip_error(int32_t device, double lo, double hi, double* seed_er
   double* d = nullptr;
   CUDA_TRY(cudaMalloc(&d, 16));
   CUDA_TRY(cudaMemset(d, 0, 16));
-  gab1::recip_error_kernel<<<64, 256>>>(lo, hi, 1 << 22, d);
-  g_launches.fetch_add(1);
+  gab1::launch_recip_error_kernel(lo, hi, 1 << 22, d);
   double h[2] = {0, 0};
   CUDA_TRY(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
   cudaFree(d);

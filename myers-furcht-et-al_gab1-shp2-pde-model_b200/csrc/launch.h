@@ -1,0 +1,45 @@
+// launch.h — what the host translation unit (gab1pde.cu) and the kernel translation units share.
+// The kernels are instantiated in their own .cu files so that the library builds in parallel.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "gab1pde.h"
+
+namespace gab1 {
+
+struct KernelArgs {
+  gab1_opts o;
+  long long S;
+  const double* Co; long long Co_stride;
+  const double* D; const double* k; const double* dt; const double* r;
+  double* out; long long out_stride;
+  int* status; int* n_saved; long long* n_steps; long long* n_bc;
+  const int* order;          // sets in descending-work order, or nullptr
+  unsigned int* counter;     // work queue head
+  double R_pow3;             // R^3.0 (libm pow on the host; sapdesolver.jl:353)
+  int P_pad;                 // doubles per staged row in shared memory
+  const int* guard;          // when non-null the kernel runs only if *guard == guard_expect (see gab1pde.cu)
+  int guard_expect;
+};
+
+enum { MODE_FAST_FOR = 0, MODE_FAST_WHILE = 1, MODE_STRICT = 2 };
+
+// thread-local error message of the C ABI (gab1_last_error); returns `code`
+int fail(int code, const char* fmt, ...);
+void count_launch();
+
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e_ = (expr);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return ::gab1::fail(-100 - (int)e_, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// one warp per parameter set, K in {1,2,4,8} nodes per lane (solver_kernel.cuh); mode is MODE_*
+int launch_single_kernel(int K, int mode, const KernelArgs& args, int device, cudaStream_t stream);
+// two parameter sets per warp, K in {1,2,4} nodes per lane of a 16-lane half (pair_kernel.cuh); fast modes only
+int launch_pair_kernel(int K, int mode, bool mirror, const KernelArgs& args, int device, cudaStream_t stream);
+// diagnostics (kernels_single.cu)
+void launch_recip_error_kernel(double lo, double hi, int n, double* out);
+
+}  // namespace gab1

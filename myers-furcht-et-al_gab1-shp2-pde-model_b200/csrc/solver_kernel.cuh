@@ -23,6 +23,7 @@
 #include <stdint.h>
 
 #include "gab1pde.h"
+#include "launch.h"
 
 namespace gab1 {
 
@@ -33,18 +34,6 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int WS_HDR = 32;          // per-warp smem header: [0,16) interior-neighbour stage, [16,32) boundary stage
 constexpr int ML = 10;              // first membrane lane
 
-struct KernelArgs {
-  gab1_opts o;
-  long long S;
-  const double* Co; long long Co_stride;
-  const double* D; const double* k; const double* dt; const double* r;
-  double* out; long long out_stride;
-  int* status; int* n_saved; long long* n_steps; long long* n_bc;
-  const int* order;          // sets in descending-work order, or nullptr
-  unsigned int* counter;     // work queue head
-  double R_pow3;             // R^3.0 (libm pow on the host; sapdesolver.jl:353)
-  int P_pad;                 // doubles per staged row in shared memory
-};
 
 // ---------------------------------------------------------------------------------------------------------------
 // strict arithmetic: a double whose operators are single IEEE operations that ptxas may not contract
@@ -300,7 +289,7 @@ __device__ __forceinline__ void kinetics_strict(const sd (&L)[NCY], const double
 
 // Membrane fixed point, strict, evaluated identically by every lane (basepdesolver.jl:197-242).
 // b[] holds the boundary values u[Nr+1,2]; m1/m2 the membrane columns [1]/[2]. Returns the iteration count.
-__device__ int membrane_strict(const KernelArgs& a, const Rates& k, double kp_now, const double (&Dsp)[NCY],
+__device__ inline int membrane_strict(const KernelArgs& a, const Rates& k, double kp_now, const double (&Dsp)[NCY],
                                const double (&In)[NCY], double (&b)[NCY], const double (&m1)[NMB], double (&m2)[NMB],
                                double dt_, unsigned& status, bool& unconverged) {
   const sd dr = a.o.dr, dt = dt_, one = 1.0, two = 2.0;
@@ -371,7 +360,6 @@ __device__ int membrane_strict(const KernelArgs& a, const Rates& k, double kp_no
 // ---------------------------------------------------------------------------------------------------------------
 // Per-set driver.  u[q][i]: species q at the lane's i-th node.
 // MODE 0: fast arithmetic, `for ... break` membrane loop; 1: fast arithmetic, `while error > tol` loop; 2: strict.
-enum { MODE_FAST_FOR = 0, MODE_FAST_WHILE = 1, MODE_STRICT = 2 };
 
 // 1/b for the Robin closures: hardware seed (MUFU.RCP64H, ~2^-20) and one cubic step r*(1 + e + e^2), e = 1 - b*r:
 // relative error ~2^-60 before the final rounding, three dependent FP64 operations, no slow-path branch.
@@ -902,6 +890,7 @@ constexpr int kWarpsPerCta = GAB1_WARPS;
 template <int K, int MODE>
 __global__ void __launch_bounds__(32 * GAB1_WARPS, (MODE == MODE_STRICT || K > 2) ? 1 : GAB1_MINB)
 solve_kernel(const KernelArgs a) {
+  if (a.guard && *a.guard != a.guard_expect) return;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* ws = smem + (size_t)warp * (WS_HDR + 2 * a.P_pad);
@@ -941,6 +930,7 @@ solve_kernel(const KernelArgs a) {
   }
 }
 
+#ifdef GAB1_WITH_DIAGNOSTICS
 // max relative error of the seed and of fast_recip over n log-spaced operands in [lo, hi] (diagnostic)
 __global__ void recip_error_kernel(double lo, double hi, int n, double* out) {
   double worst_seed = 0.0, worst = 0.0;
@@ -961,5 +951,6 @@ __global__ void recip_error_kernel(double lo, double hi, int n, double* out) {
     atomicMax((unsigned long long*)&out[1], (unsigned long long)__double_as_longlong(worst));
   }
 }
+#endif
 
 }  // namespace gab1
