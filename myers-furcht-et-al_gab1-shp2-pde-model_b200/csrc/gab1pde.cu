@@ -34,9 +34,6 @@ int fail(int code, const char* fmt, ...) {
 void count_launch() { g_launches.fetch_add(1); }
 }  // namespace gab1
 
-#ifndef GAB1_PAIRS_DEFAULT
-#define GAB1_PAIRS_DEFAULT false
-#endif
 
 namespace {
 using gab1::fail;
@@ -63,18 +60,33 @@ int pick_K(int Nr) {
     if (Nr <= 32 * K) return K;
   return 0;
 }
-// nodes per lane for the two-sets-per-warp kernels: nodes 1..Nr over 16 lanes (0: grid too large for a half warp)
-int pick_pair_K(int Nr) {
-  for (int K : {1, 2, 4})
-    if (Nr <= 16 * K) return K;
-  return 0;
-}
-// GAB1_KERNEL=pair / single selects the kernel family for grids of up to 64 nodes (A/B measurements)
-bool pairs_enabled() {
+// Which fast kernel serves a grid (measured on B200):
+//   Nr <= 32        two sets per warp, skewed loop (pair_kernel.cuh, HW = 16)        1.23x over the legacy kernel at Nr = 25
+//   32 < Nr <= 128  the first-generation one-set-per-warp kernel (solver_kernel.cuh)  best at Nr = 40, 50, 100
+//   128 < Nr <= 256 one set per warp, skewed loop (pair_kernel.cuh, HW = 32, K = 8)   1.45x over legacy at Nr = 200
+// hw = lanes per parameter set (16: two sets per warp; 32: one; 0: legacy), K = nodes per lane, variant: 0 skewed loop,
+// 1 plain loop, 2 plain loop with the interior token.  GAB1_KERNEL = legacy | group16 | group16p | group32 | group32p |
+// group32t overrides the choice where the named family can hold the grid (A/B measurements).
+struct FastPick { int hw, K, variant; };
+FastPick pick_fast(int Nr) {
+  auto fit = [&](int hw) -> int {
+    for (int K : {1, 2, 4, 8}) {
+      if (hw == 16 && K == 8) break;
+      if (hw == 32 && K == 1) continue;
+      if (Nr <= hw * K) return K;
+    }
+    return 0;
+  };
   const char* e = getenv("GAB1_KERNEL");
-  if (e && strcmp(e, "single") == 0) return false;
-  if (e && strcmp(e, "pair") == 0) return true;
-  return GAB1_PAIRS_DEFAULT;
+  if (e && strcmp(e, "legacy") == 0) return {0, 0, 0};
+  if (e && strcmp(e, "group16") == 0 && fit(16)) return {16, fit(16), 0};
+  if (e && strcmp(e, "group16p") == 0 && fit(16) == 4) return {16, 4, 1};
+  if (e && strcmp(e, "group32") == 0 && fit(32)) return {32, fit(32), 0};
+  if (e && strcmp(e, "group32p") == 0 && fit(32) == 2) return {32, 2, 1};
+  if (e && strcmp(e, "group32t") == 0 && fit(32) == 2) return {32, 2, 2};
+  if (Nr <= 32) return {16, fit(16), 0};
+  if (Nr <= 128) return {0, 0, 0};
+  return {32, fit(32), 0};
 }
 
 // ---- descending-work ordering: key = number of time steps, largest first -------------------------------------
@@ -165,12 +177,13 @@ int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long 
   const bool degenerate = o->bc_loop == GAB1_BC_FOR_BREAK && o->maxiters == 0;
   const int mode = (o->arith == 1 || degenerate) ? gab1::MODE_STRICT
                    : (o->bc_loop == GAB1_BC_WHILE ? gab1::MODE_FAST_WHILE : gab1::MODE_FAST_FOR);
-  // ---- grids that fit a half warp: two sets per warp (pair_kernel.cuh) ----
-  const int KP = (mode != gab1::MODE_STRICT && pairs_enabled()) ? pick_pair_K(o->Nr) : 0;
-  if (KP) {
+  // ---- fast arithmetic: the skewed kernels of pair_kernel.cuh ----
+  const FastPick fp = mode != gab1::MODE_STRICT ? pick_fast(o->Nr) : FastPick{0, 0, 0};
+  if (fp.K) {
     const bool mirror = o->geometry != GAB1_GEOM_SPHERICAL;
     if (!mirror) { a.guard = (const int*)(w.counter + 1); a.guard_expect = 0; }
-    const int rc = gab1::launch_pair_kernel(KP, mode, mirror, a, device, stream);
+    const int rc = fp.hw == 16 ? gab1::launch_group16_kernel(fp.K, fp.variant, mode, mirror, a, device, stream)
+                               : gab1::launch_group32_kernel(fp.K, fp.variant, mode, mirror, a, device, stream);
     if (rc || mirror) return rc;
     a.guard_expect = 1;          // the general kernel below runs only if the pair kernel declined the grid
   }

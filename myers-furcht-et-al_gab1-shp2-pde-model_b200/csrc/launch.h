@@ -37,8 +37,11 @@ void count_launch();
 
 // one warp per parameter set, K in {1,2,4,8} nodes per lane (solver_kernel.cuh); mode is MODE_*
 int launch_single_kernel(int K, int mode, const KernelArgs& args, int device, cudaStream_t stream);
-// two parameter sets per warp, K in {1,2,4} nodes per lane of a 16-lane half (pair_kernel.cuh); fast modes only
-int launch_pair_kernel(int K, int mode, bool mirror, const KernelArgs& args, int device, cudaStream_t stream);
+// skewed fast kernels (pair_kernel.cuh), fast modes only: two parameter sets per warp with K in {1,2,4} nodes per
+// lane of a 16-lane group, or one set per warp with K in {2,4,8}
+// variant: 0 = skewed loop, 1 = plain loop, 2 = plain loop with the interior token (where instantiated)
+int launch_group16_kernel(int K, int variant, int mode, bool mirror, const KernelArgs& args, int device, cudaStream_t stream);
+int launch_group32_kernel(int K, int variant, int mode, bool mirror, const KernelArgs& args, int device, cudaStream_t stream);
 // diagnostics (kernels_single.cu)
 void launch_recip_error_kernel(double lo, double hi, int n, double* out);
 

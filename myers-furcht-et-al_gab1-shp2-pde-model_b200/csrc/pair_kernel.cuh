@@ -1,5 +1,6 @@
-// pair_kernel.cuh — the product kernel for grids of up to 64 nodes (dr >= 0.2 at R = 10: BASELINE configs 2, 3, 4):
-// TWO parameter sets per warp, one per 16-lane half.
+// pair_kernel.cuh — the product kernels (fast arithmetic): one parameter set per GROUP of HW lanes, HW = 16 (two
+// sets per warp, grids of up to 64 nodes) or HW = 32 (one set per warp, up to 256 nodes).  Below, "half" means
+// such a group; with HW = 32 there is a single one and every per-half vote degenerates to a warp vote.
 //
 // Why pairs.  The one-set-per-warp kernel (solver_kernel.cuh) spends, per time step of one set, ~190 FP64 warp
 // instructions, ~62 shuffles and a serial membrane fixed point whose lanes are mostly idle; ncu (profiles/r1_*) shows
@@ -13,6 +14,15 @@
 //     cp_i = 1 + dr/r_i, cm_i = 1 - dr/r_i   (spherical; both 1 for the planar Laplacian)
 // (algebraically the reference's D*(1/(r*dr)*(u[i+1]-u[i-1]) + (u[i+1]-2u[i]+u[i-1])/dr^2)*dt + u, basepdesolver.jl:151).
 //
+// Skew.  The membrane fixed point of step n needs only u[Nr-1](n), and of everything the interior computes for step
+// n+1 only u[Nr-1](n+1) needs its result b(n) — through the single term lam_q*cp*b(n).  So one loop iteration runs
+//     interior(n+1) for every node, with the boundary contribution to node Nr-1 left out,
+//     membrane(n) — two passes in straight-line code, further passes in a (rare) loop,
+//     u[Nr-1](n+1) += lam_q*cp*b(n)
+// in ONE instruction stream: the long dependent chain of the fixed point hides behind the interior's FP64 work instead
+// of stalling the warp.  Whenever a half has an event the pipeline is drained (membrane(n+1) runs alone) so that
+// outputs see one consistent time level; the order of the arithmetic of a set does not depend on its partner.
+//
 // The two halves run the same instruction stream on their own parameter set, clock, snapshot schedule and
 // fixed-point iteration count; everything rare (snapshot due, pulse-chase switch, last step, diverged state) is
 // resolved per half behind one warp-wide countdown with the reference's exact floating-point tests.
@@ -24,12 +34,13 @@
 // Reference: basepdesolver.jl:149-296, basepdesolver_rect.jl:131-161, sapdesolver.jl:128-242,
 // sapdesolver_memb-SFK.jl:175-222, pulsechase_solver.jl:156-158.
 #pragma once
+#ifdef GAB1_PHASE_TIMING
+#include <cstdio>
+#endif
 #include "solver_kernel.cuh"
 
 namespace gab1 {
 
-constexpr int HW = 16;                     // lanes per parameter set
-constexpr unsigned HMASK = 0xffffu;
 
 template <int K>
 struct PGrid {
@@ -39,11 +50,13 @@ struct PGrid {
   int G;
 };
 
-__device__ __forceinline__ double shfl16_down1(double x) {
+template <int HW>
+__device__ __forceinline__ double shflg_down1(double x) {
   const int lo = __shfl_down_sync(FULL, __double2loint(x), 1, HW), hi = __shfl_down_sync(FULL, __double2hiint(x), 1, HW);
   return __hiloint2double(hi, lo);
 }
-__device__ __forceinline__ double shfl16_up1(double x) {
+template <int HW>
+__device__ __forceinline__ double shflg_up1(double x) {
   const int lo = __shfl_up_sync(FULL, __double2loint(x), 1, HW), hi = __shfl_up_sync(FULL, __double2hiint(x), 1, HW);
   return __hiloint2double(hi, lo);
 }
@@ -53,6 +66,54 @@ __device__ __forceinline__ long long bcast_ll(long long v, int src) {
 __device__ __forceinline__ double* bcast_ptr(double* v, int src) {
   return reinterpret_cast<double*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(v), src));
 }
+
+__device__ __forceinline__ double2 lds2(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts2(unsigned addr, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Interior token.  A scheduler holds two of these warps (255 registers each).  Left alone they drift into phase:
+// both run their FP64-dense interior update at once and share the pipe, then both sit in the latency-bound membrane
+// fixed point and leave it idle (ncu: pipe ~50% busy, per-warp period I + M with I doubled by the sharing).  The
+// token makes the two warps of a scheduler take turns at the interior, so that each warp's fixed point runs under
+// its partner's interior: period max(I_a + I_b, I + M) with I at its stand-alone speed.
+// Two named barriers per pair carry the token (bar.arrive = hand over, bar.sync = wait for it); a flag word per warp,
+// published before each hand-over, tells the partner when a warp has run out of parameter sets, so that the pair
+// stops shaking hands at the same round.
+struct Token {
+  int bar_wait, bar_post;
+  volatile int* mine;
+  volatile int* peer;
+  bool leader;            // the warp of the pair that takes the first turn
+  bool published;         // what this warp last told its partner about being out of work
+  bool peer_done;         // what the partner last told this warp
+
+  __device__ __forceinline__ void acquire() {
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_wait) : "memory");
+    peer_done = *peer != 0;
+  }
+  __device__ __forceinline__ void release(bool out_of_work) {
+    *mine = out_of_work ? 1 : 0;
+    published = out_of_work;
+    __threadfence_block();
+    asm volatile("bar.arrive %0, 64;" ::"r"(bar_post) : "memory");
+  }
+  // after the last parameter set: keep taking (empty) turns until the partner has run out of work as well
+  __device__ void drain() {
+    for (;;) {
+      const bool was_published = published;
+      acquire();
+      if (!leader && peer_done && was_published) return;       // the leader leaves after this round: so do we
+      release(true);
+      if (leader && peer_done) return;                          // both out of work as of this round
+    }
+  }
+};
 
 // lanes of the owning half stage one row into shared memory; the whole warp then stores it unit-stride
 template <int K, typename F>
@@ -68,20 +129,22 @@ __device__ __forceinline__ void pstage_row(double* row, bool mine, const PGrid<K
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-template <int K, int MODE, bool MIRROR>
-__device__ void solve_pair(const KernelArgs& a, long long item, int lane, double* ws, const PGrid<K>& g) {
+template <int K, int MODE, bool MIRROR, int HW, bool SKEW, bool TOKEN>
+__device__ void solve_pair(const KernelArgs& a, long long item, int lane, double* ws, const PGrid<K>& g, Token& tok) {
   constexpr bool WHILE = MODE == MODE_FAST_WHILE;
-  const int hl = lane & (HW - 1), hbase = lane & HW, half = lane >> 4;
+  constexpr int NH = 32 / HW;                                   // parameter sets per warp
+  constexpr unsigned HMASK = HW == 32 ? 0xffffffffu : 0xffffu;  // the lanes of one set, shifted down to bit 0
+  const int hl = lane & (HW - 1), hbase = lane & (32 - HW), half = lane / HW;
   const int Nr = a.o.Nr, P = Nr + 1, Cn = a.o.Nts + 1;
-  double* rowA = ws + 2 * WS_HDR;
+  double* rowA = ws + NH * WS_HDR;
   double* rowB = rowA + a.P_pad;
   const unsigned wsh = (unsigned)__cvta_generic_to_shared(ws) + (unsigned)(half * WS_HDR * 8);
 
   // ---- which parameter set this half solves (an odd tail leaves the second half without one: it shadows its
   //      partner's parameters and writes nothing) ----
-  const long long idx = 2 * item + half;
+  const long long idx = NH * item + half;
   const bool have = idx < a.S;
-  const long long pidx = have ? idx : 2 * item;
+  const long long pidx = have ? idx : NH * item;
   const long long set = a.order ? (long long)a.order[pidx] : pidx;
   double* oset = a.out + set * a.out_stride;
   unsigned status = 0;
@@ -122,7 +185,9 @@ __device__ void solve_pair(const KernelArgs& a, long long item, int lane, double
   double u[NCY][K];
 #pragma unroll
   for (int i = 0; i < K; ++i) {
-    const bool on = g.node[i] >= 1 && g.node[i] <= Nr && Nt > 0;      // Nt == 0: column 2 is still zero (sapdesolver.jl:245)
+    // Nt == 0: column 2 is still zero (sapdesolver.jl:245).  Node Nr is not kept on the grid while the loop runs:
+    // its slot holds zero and its value lives in the closure lanes (xc)
+    const bool on = g.node[i] >= 1 && g.node[i] <= (SKEW ? Nr - 1 : Nr) && Nt > 0;
 #pragma unroll
     for (int q = 0; q < NCY; ++q) u[q][i] = 0.0;
     u[iSFK][i] = on ? CoSFK : 0.0;      // basepdesolver.jl:137-140
@@ -220,6 +285,25 @@ __device__ void solve_pair(const KernelArgs& a, long long item, int lane, double
     default: break;
   }
   f_src += hbase;
+  // what b contributes to node Nr-1 in the next interior update: lam_q * cp(Nr-1) * b
+  double lcp = 0.0, b0 = 0.0;          // b0: u[Nr](0) = Co, the initial column (basepdesolver.jl:137-140)
+  {
+    const double cpb = a.o.geometry == GAB1_GEOM_SPHERICAL ? 1.0 + a.o.dr / a.r[Nr - 1] : 1.0;
+    switch (hl) {
+      case iSFK: lcp = l_Si; b0 = CoSFK; break;
+      case aSFK: lcp = l_Sa; break;
+      case GAB1: lcp = l_G1; b0 = CoG1; break;
+      case pGAB1: lcp = l_G1; break;
+      case GRB2: lcp = l_G2; b0 = CoG2; break;
+      case G2G1: case G2PG1: lcp = l_G2G1; break;
+      case SHP2: lcp = l_S2; b0 = CoS2; break;
+      case PG1S: lcp = l_G1S2; break;
+      case G2PG1S: lcp = l_G2G1S2; break;
+      default: break;
+    }
+    lcp *= cpb;
+    if (Nr < 2) lcp = 0.0;
+  }
   const double tol = a.o.tol;
   const bool untracked_c = hl >= NCY, untracked_m = hl >= NMB;
   const unsigned iq_addr = wsh + 8u * (unsigned)(hl < NCY ? hl : 10);       // stage slots 10..15 stay zero
@@ -399,214 +483,424 @@ __device__ void solve_pair(const KernelArgs& a, long long item, int lane, double
   {
     const unsigned b0 = __ballot_sync(FULL, !done && Nt == 0);
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h)
+    for (int h = 0; h < NH; ++h)
       if ((b0 >> (HW * h)) & 1u) finalize(h);
   }
+
+  // ---- the membrane block in pieces, so that the loop can weave it into the interior update ----
+  struct Pro { double base, A_t, B_t, rden1, Mn1; };
+  // everything that depends only on old-time membrane values (basepdesolver.jl:220-231, the terms without b)
+  auto prologue = [&]() -> Pro {
+    Pro p;
+    const double m_old = xm;
+    const double m_next = shflg_down1<HW>(m_old);
+    const double f = fma(m_old, fma(alpha2, m_old, alpha), -__dmul_rn(beta, m_next));
+    p.base = fma(s_own_t, f, fma(s_src_t, shfl(f, f_src), m_old));
+    // the first iterate of the membrane column is the old-time column: these two shuffles serve both the old-time
+    // flux coefficients and the first pass of the fixed point
+    const double Md1 = shfl(m_old, src_den);
+    p.Mn1 = shfl(m_old, src_num);
+    p.A_t = __dmul_rn(kf_t, Md1);                                 // F = dt*(kf*M_den*b - kr*M_num), old-time M
+    p.B_t = __dmul_rn(kr_t, p.Mn1);
+    p.rden1 = fast_recip(fma(cf, Md1, 1.0));                      // 1/(1 + cf*M_den) of the first pass
+    return p;
+  };
+  // Robin closure from the current membrane iterate (basepdesolver.jl:206-215)
+  auto closure = [&](double Iq, double cr) -> double {
+    const double Mn = shfl(xm, src_num);
+    const double Md = shfl(xm, src_den);
+    return __dmul_rn(fma(cr, Mn, Iq), fast_recip(fma(cf, Md, 1.0)));
+  };
+  // membrane species from the closure values of this pass (basepdesolver.jl:220-231)
+  auto membrane = [&](const Pro& p, double qv) -> double {
+    const double F = fma(p.A_t, qv, -p.B_t);
+    const double F0 = shfl(F, fs0), F1 = shfl(F, fs1), F2 = shfl(F, fs2), F3 = shfl(F, fs3);
+    return fma(sa, fma(sb, __dadd_rn(__dadd_rn(F1, F2), F3), F0), p.base);
+  };
+  // this lane's verdict on one pass: `go` = its value asks for another pass, `nanl` = the reference's error is NaN
+  auto judge = [&](double qv, double mnew, bool& go, bool& nanl) {
+    nanl = false;
+    if constexpr (!WHILE) {
+      // |1 - new/old| <= tol  <=>  |old - new| <= tol*|old|; the strict `<` also rejects old = new = 0 (0/0 = NaN
+      // in the reference) and old = +-Inf, so no special cases remain; NaN operands compare false
+      const bool okc = (fabs(__dsub_rn(xc, qv)) < __dmul_rn(tol, fabs(xc))) || untracked_c;
+      const bool okm = (fabs(__dsub_rn(xm, mnew)) < __dmul_rn(tol, fabs(xm))) || untracked_m;
+      go = !(okc && okm);
+    } else {
+      // `while error > tol`: a NaN error leaves the loop, so NaN has to be told apart exactly
+      const bool spc = !untracked_c && (is_special(xc) || is_special(qv));
+      const bool spm = !untracked_m && (is_special(xm) || is_special(mnew));
+      int clc, clm;
+      if (__any_sync(FULL, spc || spm)) {
+        clc = untracked_c ? 0 : classify_exact(xc, qv, tol);
+        clm = untracked_m ? 0 : classify_exact(xm, mnew, tol);
+      } else {
+        clc = (!untracked_c && !(fabs(__dsub_rn(xc, qv)) <= __dmul_rn(tol, fabs(xc)))) ? 1 : 0;
+        clm = (!untracked_m && !(fabs(__dsub_rn(xm, mnew)) <= __dmul_rn(tol, fabs(xm)))) ? 1 : 0;
+      }
+      go = clc == 1 || clm == 1;
+      nanl = clc == 2 || clm == 2;
+    }
+  };
+  bool unconv = false, nan_exit = false;
+  // does this half need another pass after pass number `pass`?  (`act`: it was still iterating in that pass)
+  auto decide = [&](bool act, bool go, bool nanl, int pass) -> bool {
+    bool more;
+    if constexpr (NH == 1) {
+      more = act && __any_sync(FULL, go);                 // `act` is warp-uniform: one set per warp
+      if constexpr (WHILE) {
+        if (act && __any_sync(FULL, nanl)) { nan_exit = true; more = false; }
+      }
+    } else {
+      const unsigned bgo = __ballot_sync(FULL, act && go);
+      more = act && ((bgo >> hbase) & HMASK) != 0u;
+      if constexpr (WHILE) {
+        const unsigned bnan = __ballot_sync(FULL, act && nanl);
+        if (act && ((bnan >> hbase) & HMASK)) { nan_exit = true; more = false; }
+      }
+    }
+    if (more && pass >= maxiters) {
+      if constexpr (WHILE) status |= GAB1_ST_ITER_CAP; else unconv = true;
+      more = false;
+    }
+    return more;
+  };
+  auto any_set = [&](bool p) -> bool {                     // p is uniform within a set
+    if constexpr (NH == 1) return p; else return __any_sync(FULL, p);
+  };
+  const unsigned st_I = wsh, st_b = wsh + 8u * 16u;     // stage: [0,16) inner-neighbour values, [16,32) boundary terms
+  // closure lanes publish lam*cp*b for node Nr-1; the lane that owns node Nr-1 adds it and hands the finished
+  // u[Nr-1] back as the inner-neighbour value of the next membrane block
+  auto fixup = [&](bool publish) {
+    if (publish && hl < NCY) sts(st_b + 8u * (unsigned)hl, __dmul_rn(lcp, xc));
+    __syncwarp();
+    if (hl == lane_i) {
+#pragma unroll
+      for (int q = 0; q < NCY; q += 2) {
+        const double2 c = lds2(st_b + 8u * (unsigned)q);
+        u[q][idx_i] = __dadd_rn(u[q][idx_i], c.x);
+        u[q + 1][idx_i] = __dadd_rn(u[q + 1][idx_i], c.y);
+        sts2(st_I + 8u * (unsigned)q, u[q][idx_i], u[q + 1][idx_i]);
+      }
+    }
+    __syncwarp();
+  };
+  // dead state: every value of the half is NaN; only the clock and the snapshot schedule still evolve.
+  // `behind`: membrane steps still to be accounted for
+  auto dead_check = [&](long long behind) -> bool {
+    bool newly = false;
+    if (any_set(unconv || nan_exit)) {
+      bool all_nan = (untracked_c || isnan(xc)) && (hl > LE || isnan(xm));
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int q = 0; q < NCY; ++q) all_nan &= !(g.node[i] >= 1 && g.node[i] <= Nr - 1) || isnan(u[q][i]);
+      const unsigned bn = __ballot_sync(FULL, all_nan);
+      newly = !(done || dead) && ((bn >> hbase) & HMASK) == HMASK;
+      if (newly) {
+        dead = true;
+        // a NaN error never passes `<= tol` (all maxiters passes run) and leaves `while error > tol` at once
+        bc_total += behind * (long long)(WHILE ? 1 : maxiters);
+      }
+    }
+    unconv = false; nan_exit = false;
+    return any_set(newly);
+  };
+  // the whole membrane block on its own (pipeline drain)
+  auto membrane_passes = [&](const Pro& p) {
+    const double Iq = lds(iq_addr);
+    const double cr = is_a ? fma(cf, Iq, __dmul_rn(cr_fixed, lds(st_I + 8u * iSFK))) : cr_fixed;
+    bool act = !(done || dead);
+    int pass = 1, it_mine = 0;
+    {
+      // first pass: the membrane iterate is still the old-time column, whose shuffles and reciprocal the prologue holds
+      const double qv = __dmul_rn(fma(cr, p.Mn1, Iq), p.rden1);
+      const double mnew = membrane(p, qv);
+      bool go, nanl;
+      judge(qv, mnew, go, nanl);
+      if (act) { xc = qv; xm = mnew; it_mine = 1; }
+      act = decide(act, go, nanl, 1);
+    }
+    while (any_set(act)) {
+      ++pass;
+      const double qv = closure(Iq, cr);
+      const double mnew = membrane(p, qv);
+      bool go, nanl;
+      judge(qv, mnew, go, nanl);
+      if (act) { xc = qv; xm = mnew; it_mine = pass; }
+      act = decide(act, go, nanl, pass);
+    }
+    bc_total += it_mine;
+  };
+  auto membrane_alone = [&]() {
+    const Pro p = prologue();
+    membrane_passes(p);
+  };
+  // node Nr on / off the grid around output code
+  auto boundary_to_grid = [&]() {
+    if (hl < NCY) sts(st_b + 8u * (unsigned)hl, xc);
+    __syncwarp();
+    if (hl == lane_b) {
+#pragma unroll
+      for (int q = 0; q < NCY; ++q) u[q][idx_b] = lds(st_b + 8u * (unsigned)q);
+    }
+    __syncwarp();
+  };
+  auto boundary_off_grid = [&]() {
+    if (hl == lane_b) {
+#pragma unroll
+      for (int q = 0; q < NCY; ++q) u[q][idx_b] = 0.0;
+    }
+  };
 
   long long ev_step = done ? NEVER : plan();
   bool compute;                 // warp-uniform: at least one half still integrates
   int countdown;
   auto arm = [&]() -> bool {    // returns false when both halves are finished
-    if (!__any_sync(FULL, !done)) return false;
-    compute = __any_sync(FULL, !done && !dead);
+    if (!any_set(!done)) return false;
+    compute = any_set(!done && !dead);
     long long e = ev_step;
-    const long long eo = bcast_ll(e, lane ^ HW);
-    if (eo < e) e = eo;
+    if constexpr (NH == 2) {
+      const long long eo = bcast_ll(e, lane ^ HW);
+      if (eo < e) e = eo;
+    }
     e = e - step + 1;
     countdown = (int)(e > 1000000000LL ? 1000000000LL : e);
     return true;
   };
   if (!arm()) return;
 
-  for (;;) {
-    if (compute) {
-      const bool zombie = done || dead;
-      // ---- membrane block prologue: everything that depends only on old-time values; it is independent of the
-      //      interior update below, so the two instruction streams interleave ----
-      const double m_old = xm;
-      const double m_next = shfl16_down1(m_old);
-      const double f = fma(m_old, fma(alpha2, m_old, alpha), -(beta * m_next));
-      const double base = fma(s_own_t, f, fma(s_src_t, shfl(f, f_src), m_old));
-      // the first iterate of the membrane column is the old-time column: these two shuffles serve both the old-time
-      // flux coefficients and the first pass of the fixed point
-      const double Md1 = shfl(m_old, src_den), Mn1 = shfl(m_old, src_num);
-      const double A_t = kf_t * Md1;                                 // F = dt*(kf*M_den*b - kr*M_num), old-time M
-      const double B_t = kr_t * Mn1;
-      const double rden1 = fast_recip(fma(cf, Md1, 1.0));            // 1/(1 + cf*M_den) of the first pass
+  // pipeline state (warp-uniform): `fresh` = the membrane is already at the time level of the interior, i.e. the
+  // membrane block of this iteration has nothing to do.  True at the start (b(0) = Co) and after every drain.
+  bool fresh = true;
+  if (SKEW && hl < NCY) sts(st_b + 8u * (unsigned)hl, __dmul_rn(lcp, b0));
+  __syncwarp();
 
-      // ---- interior (basepdesolver.jl:150-180), in place, left to right; `carry` is cm_i*u[i-1] of the old level ----
-      {
-        double hr[NCY], carry[NCY];
+  // plain interior update of every node this lane holds (the skewed loop below carries its own copy, woven with
+  // the membrane block); basepdesolver.jl:150-180, in place, left to right; `carry` = cm_i*u[i-1] of the old level
+  auto interior_update = [&]() {
+    double hr[NCY], carry[NCY];
+#pragma unroll
+    for (int q = 0; q < NCY; ++q) {
+      carry[q] = g.cm[0] * shflg_up1<HW>(u[q][K - 1]);
+      hr[q] = shflg_down1<HW>(u[q][0]);
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      const double Si = u[iSFK][i], Sa = u[aSFK][i], G1 = u[GAB1][i], pG1 = u[pGAB1][i], G2 = u[GRB2][i],
+                   g2g1 = u[G2G1][i], g2pg1 = u[G2PG1][i], S2 = u[SHP2][i], pg1s = u[PG1S][i], g2pg1s = u[G2PG1S][i];
+      const double gb = kG1f_t * G2, ph = kG1p_t * Sa, sbd = kS2f_t * S2;
+      const double v1 = fma(gb, G1, -(kG1r_t * g2g1));        // GRB2 + GAB1   <-> G2G1
+      const double v3 = fma(gb, pG1, -(kG1r_t * g2pg1));      // GRB2 + pGAB1  <-> G2PG1
+      const double v5 = fma(gb, pg1s, -(kG1r_t * g2pg1s));    // GRB2 + PG1S   <-> G2PG1S
+      const double v2 = fma(ph, G1, -(kG1dp_t * pG1));        // GAB1  <-> pGAB1 (aSFK / phosphatase)
+      const double v6 = fma(ph, g2g1, -(kG1dp_t * g2pg1));    // G2G1  <-> G2PG1
+      const double v4 = fma(sbd, pG1, -(kS2r_t * pg1s));      // SHP2 + pGAB1  <-> PG1S
+      const double v7 = fma(sbd, g2pg1, -(kS2r_t * g2pg1s));  // SHP2 + G2PG1  <-> G2PG1S
+      double ks[NCY];                                          // c_q*u + kinetics
+      ks[iSFK] = fma(c_Si, Si, kSi_t * Sa);                    // aSFK -> iSFK
+      ks[aSFK] = c_Sa * Sa;                                    // (the decay -kSi*aSFK is folded into c_Sa)
+      ks[GAB1] = fma(c_G1, G1, -(v1 + v2));
+      ks[pGAB1] = fma(c_G1, pG1, (v2 - v3) - v4);
+      ks[GRB2] = fma(c_G2, G2, -((v1 + v3) + v5));
+      ks[G2G1] = fma(c_G2G1, g2g1, v1 - v6);
+      ks[G2PG1] = fma(c_G2G1, g2pg1, (v3 + v6) - v7);
+      ks[SHP2] = fma(c_S2, S2, -(v4 + v7));
+      ks[PG1S] = fma(c_G1S2, pg1s, v4 - v5);
+      ks[G2PG1S] = fma(c_G2G1S2, g2pg1s, v5 + v7);
+      const double lam[NCY] = {l_Si, l_Sa, l_G1, l_G1, l_G2, l_G2G1, l_G2G1, l_S2, l_G1S2, l_G2G1S2};
+#pragma unroll
+      for (int q = 0; q < NCY; ++q) {
+        const double up = i + 1 < K ? u[q][i + 1] : hr[q];
+        double nb = fma(g.cp[i], up, carry[q]);
+        if constexpr (MIRROR) nb = fma(g.m1[i], u[q][i], nb);
+        if (i + 1 < K) carry[q] = g.cm[i + 1] * u[q][i];
+        u[q][i] = fma(lam[q], nb, ks[q]);
+      }
+    }
+  };
+
+#ifdef GAB1_PHASE_TIMING
+  long long ph_wait = 0, ph_int = 0, ph_mem = 0, ph_n = 0;
+  const long long ph_t0 = clock64();
+#endif
+  for (;;) {
+    if constexpr (!SKEW) {
+      // ===== plain order: interior(step), then membrane(step) on its own.  Leaner in registers and instructions; the
+      //       fixed point's latency is covered by the other resident warps instead of by this warp's own interior =====
+      if (compute) {
+#ifdef GAB1_PHASE_TIMING
+        const long long c0 = clock64();
+#endif
+        // old-time part of the membrane block first: its shuffles and the first reciprocal are in flight while the
+        // interior runs (and while this warp waits for its turn)
+        const Pro p = prologue();
+        if constexpr (TOKEN) tok.acquire();
+#ifdef GAB1_PHASE_TIMING
+        const long long c1 = clock64();
+#endif
+        interior_update();
+#ifdef GAB1_PHASE_TIMING
+        const long long c2 = clock64();
+#endif
+        if constexpr (TOKEN) tok.release(false);
+        if (hl == lane_i) {
+#pragma unroll
+          for (int q = 0; q < NCY; q += 2) sts2(st_I + 8u * (unsigned)q, u[q][idx_i], u[q + 1][idx_i]);
+        }
+        __syncwarp();
+        membrane_passes(p);
+        boundary_to_grid();
+        if (dead_check(Nt - step)) countdown = 1;
+#ifdef GAB1_PHASE_TIMING
+        const long long c3 = clock64();
+        ph_wait += c1 - c0; ph_int += c2 - c1; ph_mem += c3 - c2; ++ph_n;
+#endif
+      }
+    } else if (compute) {
+      // ===== one iteration: interior(step) woven with membrane(step-1), then the boundary term of node Nr-1 =====
+      const bool act0 = !(done || dead) && !fresh;
+      const double Iq = lds(iq_addr);
+      const double cr = is_a ? fma(cf, Iq, __dmul_rn(cr_fixed, lds(st_I + 8u * iSFK))) : cr_fixed;
+      const Pro p = prologue();
+      const double qv1 = __dmul_rn(fma(cr, p.Mn1, Iq), p.rden1);            // pass 1: closures
+      double m1 = 0.0, qv2 = 0.0, m2 = 0.0;
+      bool go1 = false, nan1 = false, go2 = false, nan2 = false, more1 = false, more2 = false;
+      int it_mine = 0;
+
+      double hr[NCY], carry[NCY];
+#pragma unroll
+      for (int q = 0; q < NCY; ++q) {
+        carry[q] = g.cm[0] * shflg_up1<HW>(u[q][K - 1]);
+        hr[q] = shflg_down1<HW>(u[q][0]);
+      }
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        // ---- a slice of the membrane block between two nodes ----
+        if (i == (K >= 4 ? 1 : 0)) {
+          m1 = membrane(p, qv1);                                            // pass 1: membrane species
+          judge(qv1, m1, go1, nan1);
+          if (act0) { xc = qv1; xm = m1; it_mine = 1; }
+          qv2 = closure(Iq, cr);                                            // pass 2: closures (used only if needed)
+        }
+        if (i == (K >= 4 ? 2 : K - 1)) {
+          more1 = decide(act0, go1, nan1, 1);
+          m2 = membrane(p, qv2);                                            // pass 2: membrane species
+          judge(qv2, m2, go2, nan2);
+          if (more1) { xc = qv2; xm = m2; it_mine = 2; }
+        }
+        // ---- interior node i (basepdesolver.jl:150-180), in place, left to right; `carry` = cm_i*u[i-1] of the old level ----
+        const double Si = u[iSFK][i], Sa = u[aSFK][i], G1 = u[GAB1][i], pG1 = u[pGAB1][i], G2 = u[GRB2][i],
+                     g2g1 = u[G2G1][i], g2pg1 = u[G2PG1][i], S2 = u[SHP2][i], pg1s = u[PG1S][i], g2pg1s = u[G2PG1S][i];
+        const double gb = kG1f_t * G2, ph = kG1p_t * Sa, sbd = kS2f_t * S2;
+        const double v1 = fma(gb, G1, -(kG1r_t * g2g1));        // GRB2 + GAB1   <-> G2G1
+        const double v3 = fma(gb, pG1, -(kG1r_t * g2pg1));      // GRB2 + pGAB1  <-> G2PG1
+        const double v5 = fma(gb, pg1s, -(kG1r_t * g2pg1s));    // GRB2 + PG1S   <-> G2PG1S
+        const double v2 = fma(ph, G1, -(kG1dp_t * pG1));        // GAB1  <-> pGAB1 (aSFK / phosphatase)
+        const double v6 = fma(ph, g2g1, -(kG1dp_t * g2pg1));    // G2G1  <-> G2PG1
+        const double v4 = fma(sbd, pG1, -(kS2r_t * pg1s));      // SHP2 + pGAB1  <-> PG1S
+        const double v7 = fma(sbd, g2pg1, -(kS2r_t * g2pg1s));  // SHP2 + G2PG1  <-> G2PG1S
+        double ks[NCY];                                          // c_q*u + kinetics
+        ks[iSFK] = fma(c_Si, Si, kSi_t * Sa);                    // aSFK -> iSFK
+        ks[aSFK] = c_Sa * Sa;                                    // (the decay -kSi*aSFK is folded into c_Sa)
+        ks[GAB1] = fma(c_G1, G1, -(v1 + v2));
+        ks[pGAB1] = fma(c_G1, pG1, (v2 - v3) - v4);
+        ks[GRB2] = fma(c_G2, G2, -((v1 + v3) + v5));
+        ks[G2G1] = fma(c_G2G1, g2g1, v1 - v6);
+        ks[G2PG1] = fma(c_G2G1, g2pg1, (v3 + v6) - v7);
+        ks[SHP2] = fma(c_S2, S2, -(v4 + v7));
+        ks[PG1S] = fma(c_G1S2, pg1s, v4 - v5);
+        ks[G2PG1S] = fma(c_G2G1S2, g2pg1s, v5 + v7);
+        const double lam[NCY] = {l_Si, l_Sa, l_G1, l_G1, l_G2, l_G2G1, l_G2G1, l_S2, l_G1S2, l_G2G1S2};
 #pragma unroll
         for (int q = 0; q < NCY; ++q) {
-          carry[q] = g.cm[0] * shfl16_up1(u[q][K - 1]);
-          hr[q] = shfl16_down1(u[q][0]);
-        }
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-          const double Si = u[iSFK][i], Sa = u[aSFK][i], G1 = u[GAB1][i], pG1 = u[pGAB1][i], G2 = u[GRB2][i],
-                       g2g1 = u[G2G1][i], g2pg1 = u[G2PG1][i], S2 = u[SHP2][i], pg1s = u[PG1S][i], g2pg1s = u[G2PG1S][i];
-          const double gb = kG1f_t * G2, ph = kG1p_t * Sa, sbd = kS2f_t * S2;
-          const double v1 = fma(gb, G1, -(kG1r_t * g2g1));        // GRB2 + GAB1   <-> G2G1
-          const double v3 = fma(gb, pG1, -(kG1r_t * g2pg1));      // GRB2 + pGAB1  <-> G2PG1
-          const double v5 = fma(gb, pg1s, -(kG1r_t * g2pg1s));    // GRB2 + PG1S   <-> G2PG1S
-          const double v2 = fma(ph, G1, -(kG1dp_t * pG1));        // GAB1  <-> pGAB1 (aSFK / phosphatase)
-          const double v6 = fma(ph, g2g1, -(kG1dp_t * g2pg1));    // G2G1  <-> G2PG1
-          const double v4 = fma(sbd, pG1, -(kS2r_t * pg1s));      // SHP2 + pGAB1  <-> PG1S
-          const double v7 = fma(sbd, g2pg1, -(kS2r_t * g2pg1s));  // SHP2 + G2PG1  <-> G2PG1S
-          double ks[NCY];                                          // c_q*u + kinetics
-          ks[iSFK] = fma(c_Si, Si, kSi_t * Sa);                    // aSFK -> iSFK
-          ks[aSFK] = c_Sa * Sa;                                    // (the decay -kSi*aSFK is folded into c_Sa)
-          ks[GAB1] = fma(c_G1, G1, -(v1 + v2));
-          ks[pGAB1] = fma(c_G1, pG1, (v2 - v3) - v4);
-          ks[GRB2] = fma(c_G2, G2, -((v1 + v3) + v5));
-          ks[G2G1] = fma(c_G2G1, g2g1, v1 - v6);
-          ks[G2PG1] = fma(c_G2G1, g2pg1, (v3 + v6) - v7);
-          ks[SHP2] = fma(c_S2, S2, -(v4 + v7));
-          ks[PG1S] = fma(c_G1S2, pg1s, v4 - v5);
-          ks[G2PG1S] = fma(c_G2G1S2, g2pg1s, v5 + v7);
-          const double lam[NCY] = {l_Si, l_Sa, l_G1, l_G1, l_G2, l_G2G1, l_G2G1, l_S2, l_G1S2, l_G2G1S2};
-#pragma unroll
-          for (int q = 0; q < NCY; ++q) {
-            const double up = i + 1 < K ? u[q][i + 1] : hr[q];
-            double nb = fma(g.cp[i], up, carry[q]);
-            if constexpr (MIRROR) nb = fma(g.m1[i], u[q][i], nb);
-            if (i + 1 < K) carry[q] = g.cm[i + 1] * u[q][i];
-            u[q][i] = fma(lam[q], nb, ks[q]);
-          }
-          if (i == idx_i) {
-            // hand the inner-neighbour values u+[Nr-1] to the closure lanes as soon as they exist
-            if (hl == lane_i) {
-#pragma unroll
-              for (int q = 0; q < NCY; ++q) sts(wsh + 8 * q, u[q][i]);
-            }
-          }
+          const double up = i + 1 < K ? u[q][i + 1] : hr[q];
+          double nb = fma(g.cp[i], up, carry[q]);
+          if constexpr (MIRROR) nb = fma(g.m1[i], u[q][i], nb);
+          if (i + 1 < K) carry[q] = g.cm[i + 1] * u[q][i];
+          u[q][i] = fma(lam[q], nb, ks[q]);
         }
       }
-      __syncwarp();
-      const double Iq = lds(iq_addr);
-      const double cr = is_a ? fma(cf, Iq, cr_fixed * lds(wsh + 8 * iSFK)) : cr_fixed;
-
-      // ---- fixed-point iterations (basepdesolver.jl:197-242), both halves in the same instructions; a half that
-      //      has finished keeps its iterate while the other one goes on ----
-      bool active = !zombie;
-      int it_mine = 0, pass = 1;
-      bool unconv = false, nan_exit = false;
-      {
-        // everything after the closure value qv of one pass; returns true when some half needs another pass
-        auto finish_pass = [&](double qv) -> bool {
-          const double F = fma(A_t, qv, -B_t);
-          const double F0 = shfl(F, fs0), F1 = shfl(F, fs1), F2 = shfl(F, fs2), F3 = shfl(F, fs3);
-          const double mnew = fma(sa, fma(sb, (F1 + F2) + F3, F0), base);
-          bool go;                      // this lane's value asks for another pass
-          bool nanl = false;
-          if constexpr (!WHILE) {
-            // |1 - new/old| <= tol  <=>  |old - new| <= tol*|old|; the strict `<` also rejects old = new = 0 (0/0 = NaN
-            // in the reference) and old = +-Inf, so no special cases remain; NaN operands compare false
-            const bool okc = (fabs(xc - qv) < tol * fabs(xc)) || untracked_c;
-            const bool okm = (fabs(xm - mnew) < tol * fabs(xm)) || untracked_m;
-            go = !(okc && okm);
-          } else {
-            // `while error > tol`: a NaN error leaves the loop, so NaN has to be told apart exactly
-            const bool spc = !untracked_c && (is_special(xc) || is_special(qv));
-            const bool spm = !untracked_m && (is_special(xm) || is_special(mnew));
-            int clc, clm;
-            if (__any_sync(FULL, spc || spm)) {
-              clc = untracked_c ? 0 : classify_exact(xc, qv, tol);
-              clm = untracked_m ? 0 : classify_exact(xm, mnew, tol);
-            } else {
-              clc = (!untracked_c && !(fabs(xc - qv) <= tol * fabs(xc))) ? 1 : 0;
-              clm = (!untracked_m && !(fabs(xm - mnew) <= tol * fabs(xm))) ? 1 : 0;
-            }
-            go = clc == 1 || clm == 1;
-            nanl = clc == 2 || clm == 2;
-          }
-          if (active) { xc = qv; xm = mnew; it_mine = pass; }
-          const unsigned bgo = __ballot_sync(FULL, active && go);
-          bool more_mine = ((bgo >> hbase) & HMASK) != 0u;
-          if constexpr (WHILE) {
-            const unsigned bnan = __ballot_sync(FULL, active && nanl);
-            if (active && ((bnan >> hbase) & HMASK)) { nan_exit = true; more_mine = false; }
-          }
-          if (active && more_mine && pass >= maxiters) {
-            if constexpr (WHILE) status |= GAB1_ST_ITER_CAP; else unconv = true;
-            more_mine = false;
-          }
-          if (!more_mine) active = false;
-          return __any_sync(FULL, active);
-        };
-        bool more = finish_pass(fma(cr, Mn1, Iq) * rden1);
-        while (more) {
+      // ---- further passes (rare: the first steps of a solve, stiff corners of parameter space) ----
+      more2 = decide(more1, go2, nan2, 2);
+      if (any_set(more2)) {
+        bool act = more2;
+        int pass = 2;
+        do {
           ++pass;
-          const double Mn = shfl(xm, src_num);
-          const double Md = shfl(xm, src_den);
-          more = finish_pass(fma(cr, Mn, Iq) * fast_recip(fma(cf, Md, 1.0)));
-        }
+          const double qv = closure(Iq, cr);
+          const double mnew = membrane(p, qv);
+          bool go, nanl;
+          judge(qv, mnew, go, nanl);
+          if (act) { xc = qv; xm = mnew; it_mine = pass; }
+          act = decide(act, go, nanl, pass);
+        } while (any_set(act));
       }
       bc_total += it_mine;
-      // ---- boundary values back to the lane that owns node Nr ----
-      if (hl < NCY) sts(wsh + 8 * (16 + hl), xc);
-      __syncwarp();
-      if (hl == lane_b) {
-#pragma unroll
-        for (int q = 0; q < NCY; ++q) u[q][idx_b] = lds(wsh + 8 * (16 + q));
-      }
-      if (__any_sync(FULL, unconv || nan_exit)) {
-        bool all_nan = (untracked_c || isnan(xc)) && (hl > LE || isnan(xm));
-#pragma unroll
-        for (int i = 0; i < K; ++i)
-#pragma unroll
-          for (int q = 0; q < NCY; ++q) all_nan &= !(g.node[i] >= 1 && g.node[i] <= Nr) || isnan(u[q][i]);
-        const unsigned bn = __ballot_sync(FULL, all_nan);
-        const bool newly = !zombie && ((bn >> hbase) & HMASK) == HMASK;
-        if (newly) {
-          dead = true;                 // only the clock and the snapshot schedule still evolve:
-          bc_total += (Nt - step) * (long long)(WHILE ? 1 : maxiters);   // a NaN error never passes `<= tol`, and leaves `while error > tol` at once
-        }
-        if (__any_sync(FULL, newly)) countdown = 1;              // re-arm: maybe nothing is left to integrate
-      }
+      fixup(!fresh);             // after a drain (and at the start) the boundary terms are already published
+      fresh = false;
+      // membrane steps `step`..Nt are still ahead of a half that turns out to be dead now
+      if (dead_check(Nt - step + 1)) countdown = 1;             // re-arm: maybe nothing is left to integrate
     }
     t = t + dt;                                                   // basepdesolver.jl:265
     if (--countdown > 0) { ++step; continue; }
 
-    // ---- rare path: exact event tests for the step just taken, per half ----
+    // ---- rare path.  Drain the pipeline: membrane(step) on its own, so that both time levels agree ----
+    if (SKEW && compute) {
+      if (!fresh) {
+        membrane_alone();
+        if (hl < NCY) sts(st_b + 8u * (unsigned)hl, __dmul_rn(lcp, xc));     // what the next fixup() adds to node Nr-1
+        __syncwarp();
+        fresh = true;
+        (void)dead_check(Nt - step);
+      }
+    }
+    // exact event tests for the step just taken, per half
     const bool my_ev = !done && step >= ev_step;
-    if (track_t) {
-      const bool save = my_ev && (a.o.save_rule == GAB1_SAVE_T_GE_TSAVE ? (t >= t_save) : (fmod((double)step, modulus_step) == 0.0));
-      const unsigned bs = __ballot_sync(FULL, save);
-      if (bs) {
+    const bool save = track_t && my_ev &&
+                      (a.o.save_rule == GAB1_SAVE_T_GE_TSAVE ? (t >= t_save) : (fmod((double)step, modulus_step) == 0.0));
+    const unsigned bs = __ballot_sync(FULL, save);
+    const unsigned bf = __ballot_sync(FULL, my_ev && step == Nt);
+    if (bs | bf) {
+      // output code reads node Nr from the grid; the published boundary terms are rewritten below
+      if constexpr (SKEW) boundary_to_grid();
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          if (!((bs >> (HW * h)) & 1u)) continue;
+      for (int h = 0; h < NH; ++h) {
+        if ((bs >> (HW * h)) & 1u) {
           const int c = __shfl_sync(FULL, nts, HW * h);
           if (c >= Cn) { if (half == h) status |= GAB1_ST_OVERFLOW; }
           else {
             if (half == h) ++nts;
             if (a.o.out_mode == GAB1_OUT_FULL) write_column(h, c);
-            else if (c == Cn - 1) {
-              if (__shfl_sync(FULL, (int)dead, HW * h)) { if (half == h) { pct_ave = CUDART_NAN; pct_memb = CUDART_NAN; } }
-              else pct_column(h);
-            }
+            else if (c == Cn - 1) pct_column(h);
           }
         }
-        if (save && a.o.save_rule == GAB1_SAVE_T_GE_TSAVE) t_save = t_save + a.o.dt_save;
+      }
+      if (save && a.o.save_rule == GAB1_SAVE_T_GE_TSAVE) t_save = t_save + a.o.dt_save;
+#pragma unroll 1
+      for (int h = 0; h < NH; ++h)
+        if ((bf >> (HW * h)) & 1u) finalize(h);
+      if constexpr (SKEW) {
+        boundary_off_grid();
+        if (hl < NCY) sts(st_b + 8u * (unsigned)hl, __dmul_rn(lcp, xc));
+        __syncwarp();
       }
     }
     if (my_ev && pulse_pending) {                                 // the test the next step would make at its start
       if (a.o.t_prechase + dt > t && t >= a.o.t_prechase) { if (hl == mESmES) alpha = 0.0; pulse_pending = false; }
       else if (t >= a.o.t_prechase + dt) pulse_pending = false;   // the window was stepped over: the reference never switches
     }
-    {
-      const unsigned bf = __ballot_sync(FULL, my_ev && step == Nt);
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h)
-        if ((bf >> (HW * h)) & 1u) finalize(h);
-    }
     ++step;
     if (done) ev_step = NEVER;
     else if (my_ev) ev_step = plan();
     if (!arm()) break;
   }
+#ifdef GAB1_PHASE_TIMING
+  if (lane == 0 && blockIdx.x == 3 && threadIdx.x < 64 && item < 3000)
+    printf("item %lld warp %d: steps %lld, per step: wait %.0f interior %.0f membrane+rest %.0f, whole loop %.0f cycles\n", item,
+           (int)(threadIdx.x >> 5), ph_n, (double)ph_wait / ph_n, (double)ph_int / ph_n, (double)ph_mem / ph_n,
+           (double)(clock64() - ph_t0) / ph_n);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -620,18 +914,34 @@ __device__ void solve_pair(const KernelArgs& a, long long item, int lane, double
 #endif
 constexpr int kPairWarpsPerCta = GAB1_PAIR_WARPS;
 
-template <int K, int MODE, bool MIRROR>
-__global__ void __launch_bounds__(32 * GAB1_PAIR_WARPS, GAB1_PAIR_MINB)
+// launch shape of the plain (non-skewed) kernels with at most 2 nodes per lane and set: warps per CTA and CTAs per SM
+#ifndef GAB1_PLAIN_WARPS
+#define GAB1_PLAIN_WARPS 4
+#endif
+#ifndef GAB1_PLAIN_MINB
+#define GAB1_PLAIN_MINB 2
+#endif
+template <int K, int HW, bool SKEW, bool TOKEN>
+struct Shape {
+  static constexpr bool small = !SKEW && K * (32 / HW) <= 2;
+  // token kernels: one CTA of eight warps per SM, warps w and w+4 share a scheduler and a token
+  static constexpr int warps = TOKEN ? 8 : small ? GAB1_PLAIN_WARPS : GAB1_PAIR_WARPS;
+  static constexpr int minb = TOKEN ? 1 : (HW == 32 && K > 2) ? 1 : small ? GAB1_PLAIN_MINB : GAB1_PAIR_MINB;
+};
+template <int K, int MODE, bool MIRROR, int HW, bool SKEW, bool TOKEN>
+__global__ void __launch_bounds__(32 * Shape<K, HW, SKEW, TOKEN>::warps, Shape<K, HW, SKEW, TOKEN>::minb)
 solve_pair_kernel(const KernelArgs a) {
+  static_assert(!(TOKEN && SKEW), "the token belongs to the plain loop");
   // the spherical stencil without the mirror term relies on cm = 1 - dr/r[1] being exactly zero; the host side
   // routes any other grid to the general kernel through this flag (set by work_keys_kernel)
   if (a.guard && *a.guard != a.guard_expect) return;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* ws = smem + (size_t)warp * (2 * WS_HDR + 2 * a.P_pad);
+  constexpr int NH = 32 / HW;
+  double* ws = smem + (size_t)warp * (NH * WS_HDR + 2 * a.P_pad);
   const int Nr = a.o.Nr;
-  ws[lane] = 0.0;
-  ws[32 + lane] = 0.0;
+#pragma unroll
+  for (int h = 0; h < NH; ++h) ws[32 * h + lane] = 0.0;
   __syncwarp();
 
   PGrid<K> g;
@@ -651,15 +961,33 @@ solve_pair_kernel(const KernelArgs a) {
       g.m1[i] = (interior && n == 1) ? 1.0 - e : 0.0;   // u[0] = u[1]: the mirror term joins the centre (basepdesolver.jl:183-192)
     }
   }
-  const long long n_items = (a.S + 1) / 2;
+  Token tok;
+  if constexpr (TOKEN) {
+    constexpr int W = Shape<K, HW, SKEW, TOKEN>::warps;
+    int* flags = reinterpret_cast<int*>(smem + (size_t)W * (NH * WS_HDR + 2 * a.P_pad));
+    if (threadIdx.x < W) flags[threadIdx.x] = 0;
+    __syncthreads();
+    const int pair = warp & 3;                      // warps w and w+4 sit on the same scheduler
+    tok.leader = warp < 4;
+    const int P = 1 + 2 * pair, Q = 2 + 2 * pair;   // P: leader -> follower, Q: follower -> leader
+    tok.bar_wait = tok.leader ? Q : P;
+    tok.bar_post = tok.leader ? P : Q;
+    tok.mine = flags + warp;
+    tok.peer = flags + (warp ^ 4);
+    tok.published = false;
+    tok.peer_done = false;
+    if (!tok.leader) asm volatile("bar.arrive %0, 64;" ::"r"(Q) : "memory");    // the leader takes the first turn
+  }
+  const long long n_items = (a.S + NH - 1) / NH;
   for (;;) {
     unsigned item = 0;
     if (lane == 0) item = atomicAdd(a.counter, 1u);
     item = __shfl_sync(FULL, item, 0);
     if ((long long)item >= n_items) break;
-    solve_pair<K, MODE, MIRROR>(a, (long long)item, lane, ws, g);
+    solve_pair<K, MODE, MIRROR, HW, SKEW, TOKEN>(a, (long long)item, lane, ws, g, tok);
     __syncwarp();
   }
+  if constexpr (TOKEN) tok.drain();
 }
 
 }  // namespace gab1

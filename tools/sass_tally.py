@@ -50,10 +50,12 @@ def main():
         print(f"hottest loop: instructions {lo}..{hi} ({hi - lo + 1}), FP64 {nfp}")
         print("  " + "; ".join(f"{o} {n}" for o, n in c.most_common(24)))
     # all loops with DFMA, innermost first
+    shown = 0
     for lo, hi in sorted(loops, key=lambda x: x[1] - x[0]):
         body = Counter(opcode(i) for _, i in rows[lo:hi + 1])
         nfp = sum(body[b] for b in fp)
-        if nfp >= 8:
+        if nfp >= 150 and shown < 4:
+            shown += 1
             print(f"  loop {lo}..{hi} len {hi-lo+1}: FP64 {nfp} SHFL {body['SHFL']} LDS {body['LDS']} STS {body['STS']} LDL {body['LDL']} STL {body['STL']} "
                   f"MOV {body['MOV']+body['IMAD']} MUFU {body['MUFU']} VOTE {body['VOTE']} BRA {body['BRA']}")
 
