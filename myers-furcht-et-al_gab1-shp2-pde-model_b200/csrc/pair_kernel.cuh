@@ -925,8 +925,15 @@ template <int K, int HW, bool SKEW, bool TOKEN>
 struct Shape {
   static constexpr bool small = !SKEW && K * (32 / HW) <= 2;
   // token kernels: one CTA of eight warps per SM, warps w and w+4 share a scheduler and a token
+#ifdef GAB1_STATIC_QUEUE
+  // experiment: one warp per CTA and a static, CTA-index-derived assignment of parameter sets, so that ptxas can
+  // prove the per-set constants warp-uniform and keep them in uniform registers
+  static constexpr int warps = 1;
+  static constexpr int minb = GAB1_STATIC_QUEUE;
+#else
   static constexpr int warps = TOKEN ? 8 : small ? GAB1_PLAIN_WARPS : GAB1_PAIR_WARPS;
   static constexpr int minb = TOKEN ? 1 : (HW == 32 && K > 2) ? 1 : small ? GAB1_PLAIN_MINB : GAB1_PAIR_MINB;
+#endif
 };
 template <int K, int MODE, bool MIRROR, int HW, bool SKEW, bool TOKEN>
 __global__ void __launch_bounds__(32 * Shape<K, HW, SKEW, TOKEN>::warps, Shape<K, HW, SKEW, TOKEN>::minb)
@@ -979,11 +986,15 @@ solve_pair_kernel(const KernelArgs a) {
     if (!tok.leader) asm volatile("bar.arrive %0, 64;" ::"r"(Q) : "memory");    // the leader takes the first turn
   }
   const long long n_items = (a.S + NH - 1) / NH;
+#ifdef GAB1_STATIC_QUEUE
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+#else
   for (;;) {
     unsigned item = 0;
     if (lane == 0) item = atomicAdd(a.counter, 1u);
     item = __shfl_sync(FULL, item, 0);
     if ((long long)item >= n_items) break;
+#endif
     solve_pair<K, MODE, MIRROR, HW, SKEW, TOKEN>(a, (long long)item, lane, ws, g, tok);
     __syncwarp();
   }

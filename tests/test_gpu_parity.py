@@ -281,3 +281,51 @@ def test_pinned_output_is_written_in_place(pkg, gfe, ensemble):
         np.testing.assert_array_equal(status, st_s)
     finally:
         pkg.abi.pinned_free(p)
+
+
+FAMILIES = {
+    # GAB1_KERNEL value -> grids (dr) it can hold; every family the library ships is checked against the oracle,
+    # not only the one the dispatcher picks for a grid (gab1pde.cu: pick_fast)
+    "legacy": [0.4, 0.2, 0.1],
+    "group16": [0.4, 0.25, 0.2],
+    "group16p": [0.2],
+    "group32": [0.2, 0.1, 0.05],
+    "group32p": [0.2],
+    "group32t": [0.2],
+}
+
+
+@pytest.mark.parametrize("family", list(FAMILIES))
+def test_every_kernel_family_matches_the_oracle(pkg, gfe, ofe, ensemble, family, monkeypatch):
+    """Same bar as test_fast_within_tolerance_full for each kernel family forced through GAB1_KERNEL: values within
+    1e-9, identical step counts, snapshot schedules, membrane-iteration counts and status words.  An odd number of sets
+    (7) leaves one half-warp of the two-sets-per-warp kernels without a partner.  (Diverging rows are left to
+    test_full_length_solves_config2_sample: on an unstable trajectory rounding differences grow exponentially, so
+    iteration counts are only comparable while a set is stable.)"""
+    monkeypatch.setenv("GAB1_KERNEL", family)
+    Co = pkg.params.base_Co()
+    rows = [0, 1, 2, 3, 4, 2500, 4999]
+    for dr in FAMILIES[family]:
+        tf = {0.4: 0.6, 0.25: 0.5, 0.2: 0.5, 0.1: 0.15, 0.05: 0.04}[dr]
+        for variant in ("pdesolver", "rect", "pulsechase", "membSFK"):
+            kw = dict(dr=dr, tf=tf, Nts=7, tol=1e-4, maxiters=20, **VARIANTS[variant])
+            res = gfe.pdesolver_batch(Co, ensemble[rows, :7], ensemble[rows, 7:], **kw)
+            ref = ofe.pdesolver_batch(Co, ensemble[rows, :7], ensemble[rows, 7:], **kw)
+            np.testing.assert_array_equal(res.n_steps, ref.n_steps)
+            np.testing.assert_array_equal(res.n_saved, ref.n_saved)
+            np.testing.assert_array_equal(res.status, ref.status)
+            good = (ref.status & pkg.abi.ST_NAN) == 0
+            np.testing.assert_array_equal(res.n_bc_iters[good], ref.n_bc_iters[good])
+            e = rel_err(res.out[good], ref.out[good])
+            assert e < RTOL, f"{family} {variant} dr={dr}: rel err {e:.3e}"
+        # the while-loop form and the final-time reductions (sapdesolver_membSFK / fbatch semantics)
+        for mode in (pkg.abi.OUT_FINAL4, pkg.abi.OUT_SIX):
+            kw = dict(dr=dr, tf=tf, membSFK=True, out_mode=mode)
+            res = gfe.sapdesolver_batch(pkg.params.hela_Co(), ensemble[rows, :7], ensemble[rows, 7:], **kw)
+            ref = ofe.sapdesolver_batch(pkg.params.hela_Co(), ensemble[rows, :7], ensemble[rows, 7:], **kw)
+            check_control_flow(res, ref)
+            if mode == pkg.abi.OUT_SIX:
+                np.testing.assert_array_equal(res.out[:, :4], ref.out[:, :4])
+                assert rel_err(res.out[:, 4:], ref.out[:, 4:]) < RTOL
+            else:
+                assert rel_err(res.out, ref.out) < RTOL
