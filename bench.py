@@ -270,6 +270,13 @@ def run_ours(args):
         lib.gab1_host_free(p)
 
     if rank == 0:
+        traffic = None          # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture
+        try:
+            tj = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
+            if not (CFG.get("sets") or args.dr):
+                traffic = tj["traffic_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
+            pass
         cpu = None
         if world == 1 and not args.no_cpu:
             v, threads, n, sec = cpu_sample(pkg)
@@ -282,7 +289,9 @@ def run_ours(args):
                 "data": "reference parameter_ensemble.csv (tests/golden/parameter_ensemble.npy); 33 of 5000 rows diverge as in the reference",
                 "config": CONFIG,
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                             "frac": achieved / peak_tf if peak_tf > 0 else None, "traffic": None,
+                             "frac": achieved / peak_tf if peak_tf > 0 else None, "traffic": traffic,
+                             "traffic_note": "dram__bytes_read+write of one launch (profiles/r1_traffic.json); the "
+                                             "algorithmic output is 2.517 GB of snapshots, inputs 1 MB: HBM is not the bound",
                              "peak_source": "DFMA micro-benchmark run live by bench.py (gab1_measure_fp64_tflops); "
                                             "2 flop per FMA; MEASURED_PEAKS.json has no FP64 entry",
                              "flops_per_launch": flops, "kernel_ms": kernel_ms,
