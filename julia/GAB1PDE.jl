@@ -88,8 +88,11 @@ end
 "Batched sibling of `sapdesolver` / `sapdesolver_membSFK` (sapdesolver.jl:55-280, sapdesolver_memb-SFK.jl:55-281)."
 function sapdesolver_batch(Co, Dmat, kmat; R=10.0, dr=0.2, tf=5.0,
                            dt=[default_dt(Dmat[j, :], kmat[j, :], dr) for j in axes(Dmat, 1)],
-                           maxiters=20, tol=1.0e-3, membSFK=false, out_mode=OUT_FINAL4, r=collect(0.0:dr:R))
-    o = make_opts(; R, dr, tf, Nts=1, maxiters=membSFK ? 1_000_000 : maxiters, tol, out_mode,
+                           maxiters=20, tol=1.0e-3, membSFK=false, out_mode=OUT_FINAL4, r=collect(0.0:dr:R),
+                           iter_cap=100_000)
+    # membSFK: the reference's `while error > tol` has no cap (sapdesolver_memb-SFK.jl:177) and spins forever on a fixed
+    # point that never meets tol; the library stops such a step after `iter_cap` passes and flags the set (ST_ITER_CAP)
+    o = make_opts(; R, dr, tf, Nts=1, maxiters=membSFK ? iter_cap : maxiters, tol, out_mode,
                   sfk_mode=membSFK ? 1 : 0, bc_loop=membSFK ? 1 : 0, pg1tot_form=membSFK ? 1 : 0)
     solve(o, Co, Dmat, kmat, Float64.(dt), r)
 end
