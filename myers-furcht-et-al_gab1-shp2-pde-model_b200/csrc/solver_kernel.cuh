@@ -515,7 +515,7 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
 #pragma unroll
         for (int i = 0; i < K; ++i)
 #pragma unroll
-          for (int q = 0; q < NCY; ++q) all_nan &= (g.node[i] < 1) || isnan(u[q][i]);
+          for (int q = 0; q < NCY; ++q) all_nan &= !(g.node[i] >= 1 && g.node[i] <= Nr) || isnan(u[q][i]);   // slots outside 1..Nr are padding
 #pragma unroll
         for (int j = 0; j < NMB; ++j) all_nan &= isnan(m2[j]);
         dead = __all_sync(FULL, all_nan);
@@ -781,7 +781,7 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
 #pragma unroll
         for (int i = 0; i < K; ++i)
 #pragma unroll
-          for (int q = 0; q < NCY; ++q) all_nan &= (g.node[i] < 1) || isnan(u[q][i]);
+          for (int q = 0; q < NCY; ++q) all_nan &= !(g.node[i] >= 1 && g.node[i] <= Nr) || isnan(u[q][i]);   // slots outside 1..Nr are padding
         dead = __all_sync(FULL, all_nan);
         if (dead) countdown = 1;
       }
