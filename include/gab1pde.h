@@ -192,6 +192,10 @@ int gab1_solve_batch_device(const gab1_opts* o, int32_t device, void* stream, in
  * solves; ranges are balanced by total step count ceil(tf/dt).  Pure host code; bounds has n_shards+1 entries. */
 int gab1_plan_shards(int64_t S, const double* dt, double tf, int32_t n_shards, int64_t* bounds);
 
+/* gab1_solve_batch keeps one slab of device memory and one stream per GPU between calls (no cudaMalloc/cudaFree per
+ * call; calls that target the same GPU take turns).  This frees them; the next call re-creates what it needs. */
+void gab1_release_device_memory(void);
+
 /* Pinned, device-mapped host allocations.  When `out` of gab1_solve_batch lives in such memory the kernels write the
  * snapshots straight into it while the time loop runs (no device copy of the output, no D2H phase). */
 void* gab1_host_alloc(size_t bytes);

@@ -192,6 +192,8 @@ def load_library():
     lib.gab1_host_alloc.restype = C.c_void_p
     lib.gab1_host_free.argtypes = [C.c_void_p]
     lib.gab1_host_free.restype = None
+    lib.gab1_release_device_memory.argtypes = []
+    lib.gab1_release_device_memory.restype = None
     lib.gab1_measure_fp64_tflops.argtypes = [C.c_int32, C.c_double]
     lib.gab1_measure_fp64_tflops.restype = C.c_double
     lib.gab1_debug_recip_error.argtypes = [C.c_int32, C.c_double, C.c_double, _dp, _dp]

@@ -280,67 +280,90 @@ int gab1_solve_batch_device(const gab1_opts* o, int32_t device, void* stream, in
                       (long long*)n_steps, (long long*)n_bc_iters, workspace);
 }
 
-// One shard of the host entry point: copy in, solve, copy out, on its own stream.
+// Per-device arena of the host entry point: one slab of device memory and one stream per GPU, created on first use,
+// grown when a call needs more and kept between calls (gab1_release_device_memory frees them), so that a call costs no
+// cudaMalloc / cudaFree.  Calls that target the same device take turns; different devices run concurrently.
+struct DeviceArena {
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  char* base = nullptr;
+  size_t cap = 0;
+};
+static DeviceArena g_arena[64];
+
+// One shard of the host entry point: copy in, solve, copy out, on its device's stream.
 static int run_shard(const gab1_opts* o, int device, int64_t lo, int64_t hi, const double* Co, int64_t Co_stride,
                      const double* D, const double* k, const double* dt, const double* r, double* out, int32_t* status,
                      int32_t* n_saved, int64_t* n_steps, int64_t* n_bc) {
   const int64_t S = hi - lo;
   if (S <= 0) return 0;
+  if (device < 0 || device >= 64) return fail(-7, "device ordinal %d out of range", device);
   CUDA_TRY(cudaSetDevice(device));
-  cudaStream_t st;
-  CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  DeviceArena& ar = g_arena[device];
+  std::lock_guard<std::mutex> lk(ar.mu);
+  if (!ar.stream) CUDA_TRY(cudaStreamCreateWithFlags(&ar.stream, cudaStreamNonBlocking));
+  cudaStream_t st = ar.stream;
   const int64_t nout = gab1_out_doubles_per_set(o);
   const size_t P = (size_t)o->Nr + 1;
-  double *dCo = nullptr, *dD = nullptr, *dk = nullptr, *ddt = nullptr, *dr_ = nullptr, *dout = nullptr;
-  int32_t *dstatus = nullptr, *dsaved = nullptr;
-  int64_t *dsteps = nullptr, *dbc = nullptr;
-  void* ws = nullptr;
-  int rc = 0;
-  auto body = [&]() -> int {
-    const size_t nCo = Co_stride ? (size_t)S * GAB1_N_CO : GAB1_N_CO;
-    CUDA_TRY(cudaMalloc(&dCo, nCo * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&dD, (size_t)S * GAB1_N_D * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&dk, (size_t)S * GAB1_N_K * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&ddt, (size_t)S * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&dr_, P * sizeof(double)));
-    // A pinned (mapped) caller buffer is written by the kernel directly: snapshot stores stream over PCIe while the
-    // time loop runs, so there is no device copy of the 0.5 MB/set output and no D2H phase.  Pageable buffers are staged.
-    double* out_direct = nullptr;
-    {
-      cudaPointerAttributes attr;
-      if (cudaPointerGetAttributes(&attr, out + lo * nout) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
-        out_direct = (double*)attr.devicePointer;
-      else
-        (void)cudaGetLastError();
-    }
-    if (!out_direct) CUDA_TRY(cudaMalloc(&dout, (size_t)S * nout * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&dstatus, (size_t)S * sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc(&dsaved, (size_t)S * sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc(&dsteps, (size_t)S * sizeof(int64_t)));
-    CUDA_TRY(cudaMalloc(&dbc, (size_t)S * sizeof(int64_t)));
-    CUDA_TRY(cudaMalloc(&ws, gab1_workspace_bytes(S)));
-    CUDA_TRY(cudaMemcpyAsync(dCo, Co + (Co_stride ? lo * Co_stride : 0), nCo * sizeof(double), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(dD, D + lo * GAB1_N_D, (size_t)S * GAB1_N_D * sizeof(double), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(dk, k + lo * GAB1_N_K, (size_t)S * GAB1_N_K * sizeof(double), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(ddt, dt + lo, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(dr_, r, P * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (int e = solve_device(o, device, st, S, dCo, Co_stride, dD, dk, ddt, dr_, out_direct ? out_direct : dout, dstatus,
-                             dsaved, (long long*)dsteps, (long long*)dbc, ws))
-      return e;
-    if (!out_direct)
-      CUDA_TRY(cudaMemcpyAsync(out + lo * nout, dout, (size_t)S * nout * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (status) CUDA_TRY(cudaMemcpyAsync(status + lo, dstatus, (size_t)S * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (n_saved) CUDA_TRY(cudaMemcpyAsync(n_saved + lo, dsaved, (size_t)S * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (n_steps) CUDA_TRY(cudaMemcpyAsync(n_steps + lo, dsteps, (size_t)S * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    if (n_bc) CUDA_TRY(cudaMemcpyAsync(n_bc + lo, dbc, (size_t)S * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    return 0;
-  };
-  rc = body();
-  cudaFree(dCo); cudaFree(dD); cudaFree(dk); cudaFree(ddt); cudaFree(dr_); cudaFree(dout);
-  cudaFree(dstatus); cudaFree(dsaved); cudaFree(dsteps); cudaFree(dbc); cudaFree(ws);
-  cudaStreamDestroy(st);
-  return rc;
+  // A pinned (mapped) caller buffer is written by the kernel directly: snapshot stores stream over PCIe while the
+  // time loop runs, so there is no device copy of the 0.5 MB/set output and no D2H phase.  Pageable buffers are staged.
+  double* out_direct = nullptr;
+  {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, out + lo * nout) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+      out_direct = (double*)attr.devicePointer;
+    else
+      (void)cudaGetLastError();
+  }
+  // carve the arena
+  const size_t nCo = Co_stride ? (size_t)S * GAB1_N_CO : GAB1_N_CO;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t at = off; off += align_up(bytes, 256); return at; };
+  const size_t oCo = take(nCo * sizeof(double)), oD = take((size_t)S * GAB1_N_D * sizeof(double)),
+               oK = take((size_t)S * GAB1_N_K * sizeof(double)), oDt = take((size_t)S * sizeof(double)),
+               oR = take(P * sizeof(double)), oSt = take((size_t)S * sizeof(int32_t)), oSv = take((size_t)S * sizeof(int32_t)),
+               oNs = take((size_t)S * sizeof(int64_t)), oBc = take((size_t)S * sizeof(int64_t)),
+               oWs = take(gab1_workspace_bytes(S)), oOut = take(out_direct ? 0 : (size_t)S * nout * sizeof(double));
+  if (off > ar.cap) {
+    if (ar.base) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(ar.base); ar.base = nullptr; ar.cap = 0; }
+    const size_t want = off + off / 8;
+    CUDA_TRY(cudaMalloc((void**)&ar.base, want));
+    ar.cap = want;
+  }
+  double *dCo = (double*)(ar.base + oCo), *dD = (double*)(ar.base + oD), *dk = (double*)(ar.base + oK),
+         *ddt = (double*)(ar.base + oDt), *dr_ = (double*)(ar.base + oR), *dout = (double*)(ar.base + oOut);
+  int32_t *dstatus = (int32_t*)(ar.base + oSt), *dsaved = (int32_t*)(ar.base + oSv);
+  int64_t *dsteps = (int64_t*)(ar.base + oNs), *dbc = (int64_t*)(ar.base + oBc);
+  void* ws = ar.base + oWs;
+  CUDA_TRY(cudaMemcpyAsync(dCo, Co + (Co_stride ? lo * Co_stride : 0), nCo * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dD, D + lo * GAB1_N_D, (size_t)S * GAB1_N_D * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dk, k + lo * GAB1_N_K, (size_t)S * GAB1_N_K * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(ddt, dt + lo, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dr_, r, P * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (int e = solve_device(o, device, st, S, dCo, Co_stride, dD, dk, ddt, dr_, out_direct ? out_direct : dout, dstatus, dsaved,
+                           (long long*)dsteps, (long long*)dbc, ws)) {
+    cudaStreamSynchronize(st);
+    return e;
+  }
+  if (!out_direct)
+    CUDA_TRY(cudaMemcpyAsync(out + lo * nout, dout, (size_t)S * nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (status) CUDA_TRY(cudaMemcpyAsync(status + lo, dstatus, (size_t)S * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (n_saved) CUDA_TRY(cudaMemcpyAsync(n_saved + lo, dsaved, (size_t)S * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (n_steps) CUDA_TRY(cudaMemcpyAsync(n_steps + lo, dsteps, (size_t)S * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  if (n_bc) CUDA_TRY(cudaMemcpyAsync(n_bc + lo, dbc, (size_t)S * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+void gab1_release_device_memory(void) {
+  for (int d = 0; d < 64; ++d) {
+    DeviceArena& ar = g_arena[d];
+    std::lock_guard<std::mutex> lk(ar.mu);
+    if (!ar.base && !ar.stream) continue;
+    if (cudaSetDevice(d) != cudaSuccess) continue;
+    if (ar.stream) { cudaStreamSynchronize(ar.stream); cudaStreamDestroy(ar.stream); ar.stream = nullptr; }
+    if (ar.base) { cudaFree(ar.base); ar.base = nullptr; ar.cap = 0; }
+  }
 }
 
 int gab1_solve_batch(const gab1_opts* o, int64_t S, const double* Co, int64_t Co_stride, const double* D, const double* k,
