@@ -192,6 +192,36 @@ int gab1_solve_batch_device(const gab1_opts* o, int32_t device, void* stream, in
  * solves; ranges are balanced by total step count ceil(tf/dt).  Pure host code; bounds has n_shards+1 entries. */
 int gab1_plan_shards(int64_t S, const double* dt, double tf, int32_t n_shards, int64_t* bounds);
 
+/*
+ * Order statistics across the parameter sets of an ensemble — what the reference's figure scripts compute from the stacked
+ * full solutions: `median(stack, dims=3)` for the whole surface and `quantile(stack[node, end, :], 0.5 -+ 0.341)` for the
+ * credible band at t = tf (run_base_model.jl:103-174).  For every selected matrix, every snapshot column c in [c0, c1) and
+ * every node, the values of the sets WITHOUT GAB1_ST_NAN (run_ensemble drops the others, get_param_posteriors.jl:155) are
+ * sorted on the device and the np statistics p[] are taken with the definitions of Julia's Statistics stdlib:
+ * p[i] in [0, 1] -> quantile(v, p[i]) (default alpha = beta = 1); p[i] < 0 -> median(v) (middle(a, b) = a/2 + b/2 for an even
+ * count, which differs from quantile(v, 0.5) in the last bit).
+ *   matrices   bit m set => matrix m (GAB1_M_*), a subset of o->matrix_mask; o->out_mode must be GAB1_OUT_FULL
+ *   q          [matrix (ascending m)][i][c - c0][node], doubles
+ *   n_valid    number of sets that entered the statistics
+ * At most 25600 sets per call (one row of all sets is sorted in shared memory).
+ *
+ * gab1_solve_ensemble_quantiles: HOST buffers; solves the ensemble on one GPU (o->device_ids[0], default 0), keeps the full
+ * result in HBM and returns only the statistics and the per-set diagnostics — 0.5 MB per set never crosses PCIe.
+ * gab1_ensemble_quantiles_device: the reduction alone, on a FULL block already resident on `device` (device pointers except
+ * `p`; `workspace` holds gab1_quantiles_workspace_bytes(S) bytes; `n_valid` is a device pointer), enqueued on `stream`.
+ */
+size_t gab1_quantiles_workspace_bytes(int64_t S);
+int gab1_ensemble_quantiles_device(const gab1_opts* o, int32_t device, void* stream, int64_t S,
+                                   const double* out, const int32_t* status, uint32_t matrices,
+                                   int32_t c0, int32_t c1, int32_t np, const double* p,
+                                   double* q, int64_t* n_valid, void* workspace);
+int gab1_solve_ensemble_quantiles(const gab1_opts* o, int64_t S,
+                                  const double* Co, int64_t Co_stride,
+                                  const double* D, const double* k, const double* dt, const double* r,
+                                  uint32_t matrices, int32_t c0, int32_t c1, int32_t np, const double* p,
+                                  double* q, int32_t* status, int32_t* n_saved,
+                                  int64_t* n_steps, int64_t* n_bc_iters, int64_t* n_valid);
+
 /* gab1_solve_batch keeps one slab of device memory and one stream per GPU between calls (no cudaMalloc/cudaFree per
  * call; calls that target the same GPU take turns).  This frees them; the next call re-creates what it needs. */
 void gab1_release_device_memory(void);

@@ -97,6 +97,34 @@ function sapdesolver_batch(Co, Dmat, kmat; R=10.0, dr=0.2, tf=5.0,
     solve(o, Co, Dmat, kmat, Float64.(dt), r)
 end
 
+"""
+    ensemble_quantiles(ensemble, Co; probs=(:median, 0.5-0.341, 0.5+0.341), matrices=(:aSFK, :PG1tot, :PG1Stot), kw...)
+
+The summary surfaces of run_base_model.jl:103-174 (`median(stack, dims=3)`, `quantile(stack[node, col, :], p)` over the sets
+run_ensemble keeps) computed on the GPU: the full solutions never leave the device.  Returns
+`(Dict(name => Array (Nr+1) × ncols × length(probs)), n_valid, r, status)`; run_ensemble's solver defaults.
+"""
+function ensemble_quantiles(ensemble, Co; probs=(:median, 0.5 - 0.341, 0.5 + 0.341), matrices=(:aSFK, :PG1tot, :PG1Stot),
+                            columns=nothing, dr=0.2, R=10.0, tf=5.0, Nts=100, tol=1e-4, maxit=20, D_inds=1:7, k_inds=8:24, kw...)
+    mask = UInt32(sum(1 << (findfirst(==(m), MATRICES) - 1) for m in matrices))
+    o = make_opts(; R, dr, tf, Nts, maxiters=maxit, tol, out_mode=OUT_FULL, matrix_mask=mask, kw...)
+    c0, c1 = columns === nothing ? (0, Nts + 1) : columns
+    S = size(ensemble, 1)
+    Dt = permutedims(Float64.(ensemble[:, D_inds])); kt = permutedims(Float64.(ensemble[:, k_inds]))
+    dt = [default_dt(ensemble[j, D_inds], ensemble[j, k_inds], dr) for j in 1:S]
+    r = collect(0.0:dr:R)
+    p = Float64[x === :median ? -1.0 : x for x in probs]
+    q = zeros(Float64, o.Nr + 1, c1 - c0, length(p), length(matrices))      # C order [matrix][p][column][node]
+    status = zeros(Int32, S); n_saved = zeros(Int32, S); n_steps = zeros(Int64, S); n_bc = zeros(Int64, S); nv = zeros(Int64, 1)
+    rc = ccall((:gab1_solve_ensemble_quantiles, LIB), Cint,
+               (Ref{Opts}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, UInt32, Int32,
+                Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+               o, S, Float64.(Co), 0, Dt, kt, dt, r, mask, c0, c1, length(p), p, q, status, n_saved, n_steps, n_bc, nv)
+    rc == 0 || error("gab1_solve_ensemble_quantiles: " * unsafe_string(ccall((:gab1_last_error, LIB), Cstring, ())))
+    order = sort(collect(matrices); by=m -> findfirst(==(m), MATRICES))
+    Dict(name => q[:, :, :, i] for (i, name) in enumerate(order)), nv[1], r, status
+end
+
 ## ---------------------------------------------------------------- single solves, reference names
 function _sol(b::Batch, j; extra=false, ncol=b.o.Nts + 1)
     mats = NamedTuple{MATRICES}(Tuple(matrix(b, n, j)[:, 1:ncol] for n in MATRICES))

@@ -194,6 +194,15 @@ def load_library():
     lib.gab1_host_free.restype = None
     lib.gab1_release_device_memory.argtypes = []
     lib.gab1_release_device_memory.restype = None
+    lib.gab1_quantiles_workspace_bytes.argtypes = [C.c_int64]
+    lib.gab1_quantiles_workspace_bytes.restype = C.c_size_t
+    lib.gab1_ensemble_quantiles_device.argtypes = [C.POINTER(Opts), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                                   C.c_uint32, C.c_int32, C.c_int32, C.c_int32, _dp, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p]
+    lib.gab1_ensemble_quantiles_device.restype = C.c_int
+    lib.gab1_solve_ensemble_quantiles.argtypes = [C.POINTER(Opts), C.c_int64, _dp, C.c_int64, _dp, _dp, _dp, _dp, C.c_uint32,
+                                                  C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _i32p, _i32p, _i64p, _i64p, _i64p]
+    lib.gab1_solve_ensemble_quantiles.restype = C.c_int
     lib.gab1_measure_fp64_tflops.argtypes = [C.c_int32, C.c_double]
     lib.gab1_measure_fp64_tflops.restype = C.c_double
     lib.gab1_debug_recip_error.argtypes = [C.c_int32, C.c_double, C.c_double, _dp, _dp]
@@ -227,6 +236,39 @@ class CudaBackend:
         if rc != 0:
             raise Gab1Error(f"gab1_solve_batch failed ({rc}): {lib.gab1_last_error().decode(errors='replace')}")
         return out, status, n_saved, n_steps, n_bc
+
+    def solve_quantiles(self, o: Opts, Co, D, k, dt, r, matrices: int, c0: int, c1: int, probs):
+        """Solve on one GPU, keep the FULL result in HBM, return order statistics across the sets (gab1pde.h)."""
+        lib = load_library()
+        o.n_devices = 1
+        o.arith = self.arith
+        D = np.ascontiguousarray(D, dtype=np.float64).reshape(-1, N_D)
+        k = np.ascontiguousarray(k, dtype=np.float64).reshape(-1, N_K)
+        S = D.shape[0]
+        Co = np.ascontiguousarray(Co, dtype=np.float64)
+        co_stride = 0 if Co.ndim == 1 else N_CO
+        dt = np.ascontiguousarray(np.broadcast_to(np.asarray(dt, dtype=np.float64), (S,)))
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        p = encode_probs(probs)
+        nm = bin(matrices).count("1")
+        q = np.zeros((nm, len(p), c1 - c0, o.Nr + 1), dtype=np.float64)
+        status = np.zeros(S, dtype=np.int32)
+        n_saved = np.zeros(S, dtype=np.int32)
+        n_steps = np.zeros(S, dtype=np.int64)
+        n_bc = np.zeros(S, dtype=np.int64)
+        n_valid = np.zeros(1, dtype=np.int64)
+        rc = lib.gab1_solve_ensemble_quantiles(C.byref(o), S, _ptr(Co, _dp), co_stride, _ptr(D, _dp), _ptr(k, _dp), _ptr(dt, _dp),
+                                               _ptr(r, _dp), matrices, c0, c1, len(p), _ptr(p, _dp), _ptr(q, _dp),
+                                               _ptr(status, _i32p), _ptr(n_saved, _i32p), _ptr(n_steps, _i64p),
+                                               _ptr(n_bc, _i64p), _ptr(n_valid, _i64p))
+        if rc != 0:
+            raise Gab1Error(f"gab1_solve_ensemble_quantiles failed ({rc}): {lib.gab1_last_error().decode(errors='replace')}")
+        return q, int(n_valid[0]), status, n_saved, n_steps, n_bc
+
+
+def encode_probs(probs) -> np.ndarray:
+    """'median' -> -1.0 (Julia's median rule), numbers in [0, 1] -> quantile(v, p)."""
+    return np.array([-1.0 if (isinstance(p, str) and p == "median") else float(p) for p in probs], dtype=np.float64)
 
 
 def plan_shards(dt, tf: float, n_shards: int) -> np.ndarray:

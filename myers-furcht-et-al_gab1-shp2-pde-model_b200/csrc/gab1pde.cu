@@ -291,10 +291,18 @@ struct DeviceArena {
 };
 static DeviceArena g_arena[64];
 
+// gab1_solve_ensemble_quantiles: the FULL result stays on the device and only order statistics come back
+struct QReq {
+  uint32_t matrices; int32_t c0, c1, np;
+  const double* p;
+  double* q;            // host: nm x np x (c1-c0) x (Nr+1)
+  int64_t* n_valid;     // host
+};
+
 // One shard of the host entry point: copy in, solve, copy out, on its device's stream.
 static int run_shard(const gab1_opts* o, int device, int64_t lo, int64_t hi, const double* Co, int64_t Co_stride,
                      const double* D, const double* k, const double* dt, const double* r, double* out, int32_t* status,
-                     int32_t* n_saved, int64_t* n_steps, int64_t* n_bc) {
+                     int32_t* n_saved, int64_t* n_steps, int64_t* n_bc, const QReq* qr = nullptr) {
   const int64_t S = hi - lo;
   if (S <= 0) return 0;
   if (device < 0 || device >= 64) return fail(-7, "device ordinal %d out of range", device);
@@ -308,7 +316,7 @@ static int run_shard(const gab1_opts* o, int device, int64_t lo, int64_t hi, con
   // A pinned (mapped) caller buffer is written by the kernel directly: snapshot stores stream over PCIe while the
   // time loop runs, so there is no device copy of the 0.5 MB/set output and no D2H phase.  Pageable buffers are staged.
   double* out_direct = nullptr;
-  {
+  if (!qr) {
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, out + lo * nout) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
       out_direct = (double*)attr.devicePointer;
@@ -324,6 +332,12 @@ static int run_shard(const gab1_opts* o, int device, int64_t lo, int64_t hi, con
                oR = take(P * sizeof(double)), oSt = take((size_t)S * sizeof(int32_t)), oSv = take((size_t)S * sizeof(int32_t)),
                oNs = take((size_t)S * sizeof(int64_t)), oBc = take((size_t)S * sizeof(int64_t)),
                oWs = take(gab1_workspace_bytes(S)), oOut = take(out_direct ? 0 : (size_t)S * nout * sizeof(double));
+  size_t nq = 0, oQ = 0, oQws = 0;
+  if (qr) {
+    nq = (size_t)__builtin_popcount(qr->matrices) * qr->np * (qr->c1 - qr->c0) * P;
+    oQ = take(nq * sizeof(double));
+    oQws = take(gab1::quantiles_workspace_bytes(S) + 256);
+  }
   if (off > ar.cap) {
     if (ar.base) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(ar.base); ar.base = nullptr; ar.cap = 0; }
     const size_t want = off + off / 8;
@@ -345,7 +359,17 @@ static int run_shard(const gab1_opts* o, int device, int64_t lo, int64_t hi, con
     cudaStreamSynchronize(st);
     return e;
   }
-  if (!out_direct)
+  if (qr) {
+    double* dq = (double*)(ar.base + oQ);
+    long long* dnv = (long long*)(ar.base + oQws);
+    if (int e = gab1::ensemble_quantiles_device(o, device, st, S, dout, dstatus, qr->matrices, qr->c0, qr->c1, qr->np, qr->p, dq,
+                                                dnv, ar.base + oQws + 256)) {
+      cudaStreamSynchronize(st);
+      return e;
+    }
+    CUDA_TRY(cudaMemcpyAsync(qr->q, dq, nq * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (qr->n_valid) CUDA_TRY(cudaMemcpyAsync(qr->n_valid, dnv, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  } else if (!out_direct)
     CUDA_TRY(cudaMemcpyAsync(out + lo * nout, dout, (size_t)S * nout * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (status) CUDA_TRY(cudaMemcpyAsync(status + lo, dstatus, (size_t)S * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (n_saved) CUDA_TRY(cudaMemcpyAsync(n_saved + lo, dsaved, (size_t)S * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -353,6 +377,33 @@ static int run_shard(const gab1_opts* o, int device, int64_t lo, int64_t hi, con
   if (n_bc) CUDA_TRY(cudaMemcpyAsync(n_bc + lo, dbc, (size_t)S * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
+}
+
+size_t gab1_quantiles_workspace_bytes(int64_t S) { return gab1::quantiles_workspace_bytes(S); }
+
+int gab1_ensemble_quantiles_device(const gab1_opts* o, int32_t device, void* stream, int64_t S, const double* out,
+                                   const int32_t* status, uint32_t matrices, int32_t c0, int32_t c1, int32_t np,
+                                   const double* p, double* q, int64_t* n_valid, void* workspace) {
+  if (int rc = check_opts(o)) return rc;
+  return gab1::ensemble_quantiles_device(o, device, (cudaStream_t)stream, S, out, status, matrices, c0, c1, np, p, q,
+                                         (long long*)n_valid, workspace);
+}
+
+int gab1_solve_ensemble_quantiles(const gab1_opts* o, int64_t S, const double* Co, int64_t Co_stride, const double* D,
+                                  const double* k, const double* dt, const double* r, uint32_t matrices, int32_t c0,
+                                  int32_t c1, int32_t np, const double* p, double* q, int32_t* status, int32_t* n_saved,
+                                  int64_t* n_steps, int64_t* n_bc_iters, int64_t* n_valid) {
+  if (int rc = check_opts(o)) return rc;
+  if (o->out_mode != GAB1_OUT_FULL) return fail(-2, "ensemble quantiles need out_mode = GAB1_OUT_FULL");
+  if (S < 1) return fail(-2, "S must be >= 1");
+  if (!Co || !D || !k || !dt || !r || !q || !p) return fail(-2, "a required buffer is NULL");
+  int visible = 0;
+  if (cudaGetDeviceCount(&visible) != cudaSuccess || visible < 1)
+    return fail(-7, "no CUDA device is visible; this library has no CPU fallback");
+  // the order statistics need every set of the ensemble on one device: a single GPU holds 3e5 full solutions at Nr = 50
+  const int device = o->device_ids ? o->device_ids[0] : 0;
+  QReq qr{matrices, c0, c1, np, p, q, n_valid};
+  return run_shard(o, device, 0, S, Co, Co_stride, D, k, dt, r, nullptr, status, n_saved, n_steps, n_bc_iters, &qr);
 }
 
 void gab1_release_device_memory(void) {

@@ -42,6 +42,11 @@ int launch_single_kernel(int K, int mode, const KernelArgs& args, int device, cu
 // variant: 0 = skewed loop, 1 = plain loop, 2 = plain loop with the interior token (where instantiated)
 int launch_group16_kernel(int K, int variant, int mode, bool mirror, const KernelArgs& args, int device, cudaStream_t stream);
 int launch_group32_kernel(int K, int variant, int mode, bool mirror, const KernelArgs& args, int device, cudaStream_t stream);
+// order statistics across the sets of a FULL result (ensemble_stats.cu); all pointers but `p` are device pointers
+size_t quantiles_workspace_bytes(long long S);
+int ensemble_quantiles_device(const gab1_opts* o, int device, cudaStream_t stream, long long S, const double* out,
+                              const int* status, unsigned matrices, int c0, int c1, int np, const double* p, double* q,
+                              long long* n_valid, void* workspace);
 // diagnostics (kernels_single.cu)
 void launch_recip_error_kernel(double lo, double hi, int n, double* out);
 

@@ -86,6 +86,27 @@ class Frontend:
             o.maxiters = int(iter_cap)
         return self._run(o, Co, Dmat, kmat, dt, dr, _grid(R, dr, r))
 
+    def ensemble_quantiles(self, ensemble, Co, *, probs=("median", 0.5 - 0.341, 0.5 + 0.341),
+                           matrices=("aSFK", "PG1tot", "PG1Stot"), columns=None, dr=0.2, R=10.0, tf=5.0, Nts=100, tol=1e-4,
+                           maxit=20, D_inds=slice(0, 7), k_inds=slice(7, 24), geometry=abi.GEOM_SPHERICAL,
+                           sfk_mode=abi.SFK_DIFFUSIBLE, pg1tot_form=abi.PG1TOT_VIA_STOT):
+        """The summary surfaces of run_base_model.jl:103-174 without the full solutions leaving the device: for each
+        matrix, `median(stack, dims=3)` / `quantile(stack[node, column, :], p)` over the sets run_ensemble would keep
+        (NaN sets dropped, get_param_posteriors.jl:155), run_ensemble's solver defaults.  Returns
+        ({name: array (len(probs), n_columns, Nr+1)}, n_valid, r, status); `columns` = (c0, c1), default all Nts+1."""
+        ensemble = np.asarray(ensemble, dtype=np.float64)
+        mask = sum(1 << abi.MATRIX_NAMES.index(m) for m in matrices)
+        o = abi.make_opts(R=R, dr=dr, tf=tf, Nts=Nts, maxiters=maxit, tol=tol, geometry=geometry, sfk_mode=sfk_mode,
+                          pg1tot_form=pg1tot_form, out_mode=abi.OUT_FULL, matrix_mask=mask)
+        c0, c1 = (0, Nts + 1) if columns is None else columns
+        Dmat = np.ascontiguousarray(ensemble[:, D_inds])
+        kmat = np.ascontiguousarray(ensemble[:, k_inds])
+        dtv = params.default_dt(Dmat, kmat, dr)
+        r = params.julia_range(dr, R)
+        q, n_valid, status, *_ = self.backend.solve_quantiles(o, Co, Dmat, kmat, dtv, r, mask, c0, c1, probs)
+        order = sorted(matrices, key=abi.MATRIX_NAMES.index)
+        return {name: q[i] for i, name in enumerate(order)}, n_valid, r, status
+
     def _run(self, o, Co, Dmat, kmat, dt, dr, r) -> BatchResult:
         Dmat = np.ascontiguousarray(Dmat, dtype=np.float64).reshape(-1, abi.N_D)
         kmat = np.ascontiguousarray(kmat, dtype=np.float64).reshape(-1, abi.N_K)

@@ -61,5 +61,35 @@ class OracleBackend:
         return out, status, n_saved, n_steps, n_bc
 
 
+    def solve_quantiles(self, o, Co, D, k, dt, r, matrices, c0, c1, probs):
+        """CPU restatement of gab1_solve_ensemble_quantiles: the oracle's FULL result, NaN sets dropped, then the order
+        statistics with the published definitions of Julia's Statistics stdlib (not in the reference tree: unpinned)."""
+        import numpy as np
+        out, status, n_saved, n_steps, n_bc = self.solve(o, Co, D, k, dt, r)
+        keep = (status & abi.ST_NAN) == 0
+        P, Cn = o.Nr + 1, o.Nts + 1
+        ms = [m for m in range(abi.N_MATRICES) if (matrices >> m) & 1]
+        p = abi.encode_probs(probs)
+        q = np.zeros((len(ms), len(p), c1 - c0, P))
+        for i, m in enumerate(ms):
+            off = abi.full_matrix_offset(o, m)
+            stack = out[keep, off:off + P * Cn].reshape(-1, Cn, P)[:, c0:c1, :]      # (sets, column, node)
+            v = np.sort(stack, axis=0)
+            n = v.shape[0]
+            for j, pj in enumerate(p):
+                if n == 0:
+                    q[i, j] = np.nan
+                elif pj < 0:                                   # median!: middle(a, b) = a/2 + b/2
+                    q[i, j] = v[(n - 1) // 2] if n % 2 else v[n // 2 - 1] / 2 + v[n // 2] / 2
+                elif n == 1:
+                    q[i, j] = v[0]
+                else:                                          # Statistics._quantile, alpha = beta = 1
+                    aleph = n * pj + (1.0 + pj * (1.0 - 1.0 - 1.0))
+                    jj = min(max(int(np.trunc(aleph)), 1), n - 1)
+                    g = min(max(aleph - jj, 0.0), 1.0)
+                    q[i, j] = v[jj - 1] + g * (v[jj] - v[jj - 1])
+        return q, int(keep.sum()), status, n_saved, n_steps, n_bc
+
+
 def frontend(nthreads: int = 0):
     return pkg.host.Frontend(OracleBackend(nthreads))

@@ -71,6 +71,20 @@ def main():
     dp, ip, lp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
     cfgs = configs(pkg, args.scale)
     for ci in [int(x) for x in args.configs.split(",")]:
+        if ci == 2:
+            # configs[1] reduced on the device: median surface and the +-1 sigma band of three matrices over all snapshots
+            ens = params.load_parameter_ensemble()
+            fe = pkg.host.Frontend(abi.CudaBackend())
+            fe.ensemble_quantiles(ens[:64], params.base_Co(), columns=(100, 101))
+            t0 = time.perf_counter()
+            res, n_valid, _, status = fe.ensemble_quantiles(ens, params.base_Co())
+            sec = time.perf_counter() - t0
+            nbytes = sum(v.nbytes for v in res.values())
+            print(json.dumps({"config": "configs[1] + on-device statistics: median, 15.9 % and 84.1 % quantiles of aSFK, PG1tot, PG1Stot "
+                                        "at all 101 snapshots x 51 nodes over the sets without NaN (gab1_solve_ensemble_quantiles)",
+                              "sets": int(ens.shape[0]), "n_valid": int(n_valid), "e2e": {"s_per_call": sec, "solves_per_s": ens.shape[0] / sec,
+                              "d2h_bytes": int(nbytes + 28 * ens.shape[0]), "full_result_bytes_kept_on_device": int(ens.shape[0]) * 3 * 51 * 101 * 8 + ens.shape[0] * 11 * 101 * 8}}), flush=True)
+            continue
         c = cfgs[ci]
         o = c["o"]
         D = np.ascontiguousarray(c["D"], dtype=np.float64)
