@@ -222,6 +222,38 @@ int gab1_solve_ensemble_quantiles(const gab1_opts* o, int64_t S,
                                   double* q, int32_t* status, int32_t* n_saved,
                                   int64_t* n_steps, int64_t* n_bc_iters, int64_t* n_valid);
 
+/*
+ * Forward-mode derivatives ("tangents") of the solve — what the reference obtains by running pdesolver_fitting on
+ * ForwardDiff dual numbers (basepdesolver.jl:674-932 is generic in T): ForwardDiff.gradient(testf, …)
+ * param_fitting+inference_finitediff.jl:128-151, the LBFGS loss under AutoForwardDiff :188-240, NUTS through
+ * turing_model :308-370.  Along each of n_dir input directions the partials of EVERY input are given as one seed row
+ *     seeds[set][d][0..29] = d/d(dir d) of [ D(7) ; k(17) ; Co(5) ; dt ]      (pdesolver_fitting's packed order, then dt)
+ * — dt is computed inside pdesolver_fitting from p (:696) and so carries partials; gab1_default_dt_tangent evaluates
+ * dt and fills slot 29 of every seed row by the same rules.  Decisions (loop exits, snapshot tests, ceil) look at the
+ * values alone, exactly as comparisons on dual numbers do, so status / n_saved / n_steps / n_bc_iters are the primal's.
+ *   out      S * (1 + n_dir) * gab1_out_doubles_per_set(o) doubles; per set: block 0 = values (same layout and
+ *            numbers as gab1_solve_batch), block 1 + d = partials of every output along direction d
+ * Supported: bc_loop = GAB1_BC_FOR_BREAK with maxiters >= 1, save_rule = GAB1_SAVE_T_GE_TSAVE, t_prechase < 0,
+ * out_mode FULL / FINAL4 / PCT_BOUND / FINAL_STATE (GAB1_OUT_SIX is piecewise constant in the parameters),
+ * Nr <= 128, 1 <= n_dir <= 64.  Anything else fails loudly (negative return).  `arith` is ignored (fast forms).
+ */
+#define GAB1_N_SEED 30
+int gab1_default_dt_tangent(int64_t S, int32_t n_dir, const double* D, const double* k, double dr,
+                            double* dt /* S */, double* seeds /* S x n_dir x 30, slot 29 written */);
+int gab1_solve_tangent(const gab1_opts* o, int64_t S, int32_t n_dir,
+                       const double* Co, int64_t Co_stride,
+                       const double* D, const double* k, const double* dt,
+                       const double* seeds, const double* r,
+                       double* out, int32_t* status, int32_t* n_saved,
+                       int64_t* n_steps, int64_t* n_bc_iters);
+/* device-resident twin (device pointers, enqueued on `stream`, workspace of gab1_workspace_bytes(S) bytes) */
+int gab1_solve_tangent_device(const gab1_opts* o, int32_t device, void* stream, int64_t S, int32_t n_dir,
+                              const double* Co, int64_t Co_stride,
+                              const double* D, const double* k, const double* dt,
+                              const double* seeds, const double* r,
+                              double* out, int32_t* status, int32_t* n_saved,
+                              int64_t* n_steps, int64_t* n_bc_iters, void* workspace);
+
 /* gab1_solve_batch keeps one slab of device memory and one stream per GPU between calls (no cudaMalloc/cudaFree per
  * call; calls that target the same GPU take turns).  This frees them; the next call re-creates what it needs. */
 void gab1_release_device_memory(void);

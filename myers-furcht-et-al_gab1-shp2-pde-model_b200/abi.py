@@ -29,6 +29,7 @@ MATRIX_NAMES = ("iSFK", "aSFK", "GRB2", "GAB1", "SHP2", "G2G1", "G2PG1", "G2PG1S
 VECTOR_NAMES = ("pE", "mE", "mES", "mESmES", "E", "EG2", "EG2G1", "EG2PG1", "EG2PG1S", "EGFR_SHP2", "t_out")
 MASK_ALL = 0xFFF
 MASK_FITTING = (1 << 1) | (1 << 9) | (1 << 7)
+N_SEED = 30          # one seed row: partials of [D(7); k(17); Co(5); dt] along one direction (gab1pde.h)
 
 
 class Opts(C.Structure):
@@ -146,6 +147,39 @@ def call_solve(fn, o: Opts, Co, D, k, dt, r, *extra):
     return rc, out, status, n_saved, n_steps, n_bc
 
 
+TANGENT_ARGTYPES = [C.POINTER(Opts), C.c_int64, C.c_int32, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _i32p, _i32p, _i64p,
+                    _i64p]
+
+
+def call_solve_tangent(fn, o: Opts, Co, D, k, dt, seeds, r, *extra):
+    """Marshal numpy arrays into a gab1_solve_tangent-shaped function.  seeds: (S, n_dir, 30).
+    Returns rc, out (S, 1 + n_dir, doubles_per_set), status, n_saved, n_steps, n_bc."""
+    D = np.ascontiguousarray(D, dtype=np.float64).reshape(-1, N_D)
+    k = np.ascontiguousarray(k, dtype=np.float64).reshape(-1, N_K)
+    S = D.shape[0]
+    seeds = np.ascontiguousarray(seeds, dtype=np.float64)
+    if seeds.ndim != 3 or seeds.shape[0] != S or seeds.shape[2] != N_SEED:
+        raise ValueError("seeds must be (S, n_dir, 30)")
+    n_dir = seeds.shape[1]
+    Co = np.ascontiguousarray(Co, dtype=np.float64)
+    co_stride = 0 if Co.ndim == 1 else N_CO
+    if Co.shape not in ((N_CO,), (S, N_CO)):
+        raise ValueError("Co must be (5,) or (S, 5)")
+    dt = np.ascontiguousarray(np.broadcast_to(np.asarray(dt, dtype=np.float64), (S,)))
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    if r.shape != (o.Nr + 1,):
+        raise IndexError(f"r has {r.shape[0]} nodes but Nr+1 = {o.Nr + 1}")
+    out = np.zeros((S, 1 + n_dir, out_doubles_per_set(o)), dtype=np.float64)
+    status = np.zeros(S, dtype=np.int32)
+    n_saved = np.zeros(S, dtype=np.int32)
+    n_steps = np.zeros(S, dtype=np.int64)
+    n_bc = np.zeros(S, dtype=np.int64)
+    rc = fn(C.byref(o), S, n_dir, _ptr(Co, _dp), co_stride, _ptr(D, _dp), _ptr(k, _dp), _ptr(dt, _dp), _ptr(seeds, _dp),
+            _ptr(r, _dp), _ptr(out, _dp), _ptr(status, _i32p), _ptr(n_saved, _i32p), _ptr(n_steps, _i64p), _ptr(n_bc, _i64p),
+            *extra)
+    return rc, out, status, n_saved, n_steps, n_bc
+
+
 class Gab1Error(RuntimeError):
     pass
 
@@ -203,6 +237,13 @@ def load_library():
     lib.gab1_solve_ensemble_quantiles.argtypes = [C.POINTER(Opts), C.c_int64, _dp, C.c_int64, _dp, _dp, _dp, _dp, C.c_uint32,
                                                   C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _i32p, _i32p, _i64p, _i64p, _i64p]
     lib.gab1_solve_ensemble_quantiles.restype = C.c_int
+    lib.gab1_solve_tangent.argtypes = TANGENT_ARGTYPES
+    lib.gab1_solve_tangent.restype = C.c_int
+    lib.gab1_solve_tangent_device.argtypes = [C.POINTER(Opts), C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64]
+    lib.gab1_solve_tangent_device.argtypes += [C.c_void_p] * 11
+    lib.gab1_solve_tangent_device.restype = C.c_int
+    lib.gab1_default_dt_tangent.argtypes = [C.c_int64, C.c_int32, _dp, _dp, C.c_double, _dp, _dp]
+    lib.gab1_default_dt_tangent.restype = C.c_int
     lib.gab1_measure_fp64_tflops.argtypes = [C.c_int32, C.c_double]
     lib.gab1_measure_fp64_tflops.restype = C.c_double
     lib.gab1_debug_recip_error.argtypes = [C.c_int32, C.c_double, C.c_double, _dp, _dp]
@@ -237,6 +278,19 @@ class CudaBackend:
             raise Gab1Error(f"gab1_solve_batch failed ({rc}): {lib.gab1_last_error().decode(errors='replace')}")
         return out, status, n_saved, n_steps, n_bc
 
+    def solve_tangent(self, o: Opts, Co, D, k, dt, seeds, r):
+        """Values and forward-mode partials along the seed directions (gab1_solve_tangent)."""
+        lib = load_library()
+        o.n_devices = self.n_devices
+        rc, out, status, n_saved, n_steps, n_bc = call_solve_tangent(lib.gab1_solve_tangent, o, Co, D, k, dt, seeds, r)
+        if rc != 0:
+            raise Gab1Error(f"gab1_solve_tangent failed ({rc}): {lib.gab1_last_error().decode(errors='replace')}")
+        return out, status, n_saved, n_steps, n_bc
+
+    def default_dt_tangent(self, D, k, dr, seeds):
+        lib = load_library()
+        return _default_dt_tangent(lib.gab1_default_dt_tangent, D, k, dr, seeds)
+
     def solve_quantiles(self, o: Opts, Co, D, k, dt, r, matrices: int, c0: int, c1: int, probs):
         """Solve on one GPU, keep the FULL result in HBM, return order statistics across the sets (gab1pde.h)."""
         lib = load_library()
@@ -264,6 +318,18 @@ class CudaBackend:
         if rc != 0:
             raise Gab1Error(f"gab1_solve_ensemble_quantiles failed ({rc}): {lib.gab1_last_error().decode(errors='replace')}")
         return q, int(n_valid[0]), status, n_saved, n_steps, n_bc
+
+
+def _default_dt_tangent(fn, D, k, dr, seeds):
+    """dt and its partials by the rules of basepdesolver.jl:696 on duals; returns (dt (S,), seeds with slot 29 filled)."""
+    D = np.ascontiguousarray(D, dtype=np.float64).reshape(-1, N_D)
+    k = np.ascontiguousarray(k, dtype=np.float64).reshape(-1, N_K)
+    seeds = np.array(seeds, dtype=np.float64, order="C", copy=True)
+    S, n_dir = seeds.shape[0], seeds.shape[1]
+    dt = np.zeros(S, dtype=np.float64)
+    if fn(S, n_dir, _ptr(D, _dp), _ptr(k, _dp), float(dr), _ptr(dt, _dp), _ptr(seeds, _dp)) != 0:
+        raise Gab1Error("default_dt_tangent failed")
+    return dt, seeds
 
 
 def encode_probs(probs) -> np.ndarray:

@@ -190,6 +190,66 @@ int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long 
   return gab1::launch_single_kernel(K, mode, a, device, stream);
 }
 
+// ---- forward-mode tangents (tangent_kernel.cuh) -------------------------------------------------------------------
+int check_tangent_opts(const gab1_opts* o, int n_dir) {
+  if (int rc = check_opts(o)) return rc;
+  if (n_dir < 1 || n_dir > 64) return fail(-2, "n_dir must be in 1..64");
+  if (o->bc_loop != GAB1_BC_FOR_BREAK) return fail(-6, "tangents: only the `for … break` membrane loop is supported");
+  if (o->maxiters < 1) return fail(-6, "tangents: maxiters must be >= 1");
+  if (o->save_rule != GAB1_SAVE_T_GE_TSAVE) return fail(-6, "tangents: only the t >= t_save snapshot rule is supported");
+  if (o->t_prechase >= 0.0) return fail(-6, "tangents: pulse-chase is not supported");
+  if (o->out_mode == GAB1_OUT_SIX) return fail(-6, "tangents: GAB1_OUT_SIX is piecewise constant in the parameters");
+  if (o->Nr > 128) return fail(-6, "tangents: Nr = %d, grids with more than 128 nodes are not supported", o->Nr);
+  return 0;
+}
+
+int solve_tangent_device(const gab1_opts* o, int device, cudaStream_t stream, long long S, int n_dir, const double* Co,
+                         long long Co_stride, const double* D, const double* k, const double* dt, const double* seeds,
+                         const double* r, double* out, int* status, int* n_saved, long long* n_steps, long long* n_bc,
+                         void* workspace) {
+  if (int rc = check_tangent_opts(o, n_dir)) return rc;
+  if (S < 0) return fail(-2, "S must be >= 0");
+  if (S == 0) return 0;
+  if (S > 30000000LL) return fail(-2, "S too large for one call");
+  if (Co_stride != 0 && Co_stride != GAB1_N_CO) return fail(-2, "Co_stride must be 0 or 5");
+  if (!Co || !D || !k || !dt || !seeds || !r || !out || !workspace) return fail(-2, "a required buffer is NULL");
+  const int K = pick_K(o->Nr);
+  CUDA_TRY(cudaSetDevice(device));
+  Workspace w;
+  carve(w, workspace, S);
+  gab1::TangentArgs ta;
+  memset(&ta, 0, sizeof ta);
+  gab1::KernelArgs& a = ta.a;
+  a.o = *o;
+  a.o.device_ids = nullptr;
+  a.S = S;
+  a.Co = Co; a.Co_stride = Co_stride; a.D = D; a.k = k; a.dt = dt; a.r = r;
+  a.out = out; a.out_stride = gab1_out_doubles_per_set(o);
+  a.status = status; a.n_saved = n_saved; a.n_steps = n_steps; a.n_bc = n_bc;
+  a.order = w.vals_out;
+  a.counter = w.counter;
+  a.R_pow3 = pow(o->R, 3.0);
+  a.P_pad = (o->Nr + 1 + 3) & ~3;
+  ta.seeds = seeds;
+  ta.n_dir = n_dir;
+  int NT = gab1::tangent_directions_per_item(K, n_dir);
+  if (const char* e = getenv("GAB1_TANGENT_NT")) {      // A/B measurements
+    const int v = atoi(e);
+    if ((v == 1) || (v == 2 && K <= 2) || (v == 4 && K == 1)) NT = v;
+  }
+  ta.groups = (n_dir + NT - 1) / NT;
+  CUDA_TRY(cudaMemsetAsync(w.counter, 0, sizeof(unsigned), stream));
+  const int tb = 256;
+  work_keys_kernel<<<(unsigned)((S + tb - 1) / tb), tb, 0, stream>>>(S, dt, o->tf, w.keys_in, w.vals_in, r, o->dr, 0,
+                                                                     (int*)(w.counter + 1));
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  size_t bytes = w.cub_bytes;
+  CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp, bytes, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)S,
+                                                     0, 32, stream));
+  return gab1::launch_tangent_kernel(K, NT, ta, device, stream);
+}
+
 // ---- FP64 peak: register-resident DFMA chains ------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* sink, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -404,6 +464,126 @@ int gab1_solve_ensemble_quantiles(const gab1_opts* o, int64_t S, const double* C
   const int device = o->device_ids ? o->device_ids[0] : 0;
   QReq qr{matrices, c0, c1, np, p, q, n_valid};
   return run_shard(o, device, 0, S, Co, Co_stride, D, k, dt, r, nullptr, status, n_saved, n_steps, n_bc_iters, &qr);
+}
+
+// One shard of gab1_solve_tangent: copy in, solve, copy out, on its device's stream (arena shared with run_shard).
+static int run_tangent_shard(const gab1_opts* o, int device, int64_t lo, int64_t hi, int n_dir, const double* Co,
+                             int64_t Co_stride, const double* D, const double* k, const double* dt, const double* seeds,
+                             const double* r, double* out, int32_t* status, int32_t* n_saved, int64_t* n_steps, int64_t* n_bc) {
+  const int64_t S = hi - lo;
+  if (S <= 0) return 0;
+  if (device < 0 || device >= 64) return fail(-7, "device ordinal %d out of range", device);
+  CUDA_TRY(cudaSetDevice(device));
+  DeviceArena& ar = g_arena[device];
+  std::lock_guard<std::mutex> lk(ar.mu);
+  if (!ar.stream) CUDA_TRY(cudaStreamCreateWithFlags(&ar.stream, cudaStreamNonBlocking));
+  cudaStream_t st = ar.stream;
+  const int64_t nout = gab1_out_doubles_per_set(o) * (1 + n_dir);
+  const size_t P = (size_t)o->Nr + 1;
+  const size_t nCo = Co_stride ? (size_t)S * GAB1_N_CO : GAB1_N_CO;
+  const size_t nSeed = (size_t)S * n_dir * GAB1_N_SEED;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t at = off; off += align_up(bytes, 256); return at; };
+  const size_t oCo = take(nCo * sizeof(double)), oD = take((size_t)S * GAB1_N_D * sizeof(double)),
+               oK = take((size_t)S * GAB1_N_K * sizeof(double)), oDt = take((size_t)S * sizeof(double)),
+               oSd = take(nSeed * sizeof(double)), oR = take(P * sizeof(double)), oSt = take((size_t)S * sizeof(int32_t)),
+               oSv = take((size_t)S * sizeof(int32_t)), oNs = take((size_t)S * sizeof(int64_t)),
+               oBc = take((size_t)S * sizeof(int64_t)), oWs = take(gab1_workspace_bytes(S)),
+               oOut = take((size_t)S * nout * sizeof(double));
+  if (off > ar.cap) {
+    if (ar.base) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(ar.base); ar.base = nullptr; ar.cap = 0; }
+    const size_t want = off + off / 8;
+    CUDA_TRY(cudaMalloc((void**)&ar.base, want));
+    ar.cap = want;
+  }
+  double *dCo = (double*)(ar.base + oCo), *dD = (double*)(ar.base + oD), *dk = (double*)(ar.base + oK),
+         *ddt = (double*)(ar.base + oDt), *dsd = (double*)(ar.base + oSd), *dr_ = (double*)(ar.base + oR),
+         *dout = (double*)(ar.base + oOut);
+  int32_t *dstatus = (int32_t*)(ar.base + oSt), *dsaved = (int32_t*)(ar.base + oSv);
+  int64_t *dsteps = (int64_t*)(ar.base + oNs), *dbc = (int64_t*)(ar.base + oBc);
+  CUDA_TRY(cudaMemcpyAsync(dCo, Co + (Co_stride ? lo * Co_stride : 0), nCo * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dD, D + lo * GAB1_N_D, (size_t)S * GAB1_N_D * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dk, k + lo * GAB1_N_K, (size_t)S * GAB1_N_K * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(ddt, dt + lo, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dsd, seeds + lo * n_dir * GAB1_N_SEED, nSeed * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dr_, r, P * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (int e = solve_tangent_device(o, device, st, S, n_dir, dCo, Co_stride, dD, dk, ddt, dsd, dr_, dout, dstatus, dsaved,
+                                   (long long*)dsteps, (long long*)dbc, ar.base + oWs)) {
+    cudaStreamSynchronize(st);
+    return e;
+  }
+  CUDA_TRY(cudaMemcpyAsync(out + lo * nout, dout, (size_t)S * nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (status) CUDA_TRY(cudaMemcpyAsync(status + lo, dstatus, (size_t)S * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (n_saved) CUDA_TRY(cudaMemcpyAsync(n_saved + lo, dsaved, (size_t)S * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (n_steps) CUDA_TRY(cudaMemcpyAsync(n_steps + lo, dsteps, (size_t)S * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  if (n_bc) CUDA_TRY(cudaMemcpyAsync(n_bc + lo, dbc, (size_t)S * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int gab1_solve_tangent_device(const gab1_opts* o, int32_t device, void* stream, int64_t S, int32_t n_dir, const double* Co,
+                              int64_t Co_stride, const double* D, const double* k, const double* dt, const double* seeds,
+                              const double* r, double* out, int32_t* status, int32_t* n_saved, int64_t* n_steps,
+                              int64_t* n_bc_iters, void* workspace) {
+  return solve_tangent_device(o, device, (cudaStream_t)stream, S, n_dir, Co, Co_stride, D, k, dt, seeds, r, out, status,
+                              n_saved, (long long*)n_steps, (long long*)n_bc_iters, workspace);
+}
+
+int gab1_solve_tangent(const gab1_opts* o, int64_t S, int32_t n_dir, const double* Co, int64_t Co_stride, const double* D,
+                       const double* k, const double* dt, const double* seeds, const double* r, double* out,
+                       int32_t* status, int32_t* n_saved, int64_t* n_steps, int64_t* n_bc_iters) {
+  if (int rc = check_tangent_opts(o, n_dir)) return rc;
+  if (S < 0) return fail(-2, "S must be >= 0");
+  if (S == 0) return 0;
+  if (!Co || !D || !k || !dt || !seeds || !r || !out) return fail(-2, "a required buffer is NULL");
+  int visible = 0;
+  if (cudaGetDeviceCount(&visible) != cudaSuccess || visible < 1)
+    return fail(-7, "no CUDA device is visible; this library has no CPU fallback");
+  int nd = o->n_devices <= 0 ? visible : o->n_devices;
+  if (nd > visible && !o->device_ids) return fail(-7, "n_devices = %d but only %d CUDA devices are visible", nd, visible);
+  if (nd > S) nd = (int)S;
+  std::vector<int> devs(nd);
+  for (int i = 0; i < nd; ++i) devs[i] = o->device_ids ? o->device_ids[i] : i;
+  std::vector<int64_t> bounds(nd + 1, 0);
+  gab1_plan_shards(S, dt, o->tf, nd, bounds.data());
+  if (nd == 1)
+    return run_tangent_shard(o, devs[0], 0, S, n_dir, Co, Co_stride, D, k, dt, seeds, r, out, status, n_saved, n_steps, n_bc_iters);
+  std::vector<int> rcs(nd, 0);
+  std::vector<std::string> msgs(nd);
+  std::vector<std::thread> th;
+  for (int g = 0; g < nd; ++g)
+    th.emplace_back([&, g]() {
+      rcs[g] = run_tangent_shard(o, devs[g], bounds[g], bounds[g + 1], n_dir, Co, Co_stride, D, k, dt, seeds, r, out, status,
+                                 n_saved, n_steps, n_bc_iters);
+      if (rcs[g]) msgs[g] = g_err;
+    });
+  for (auto& t : th) t.join();
+  for (int g = 0; g < nd; ++g)
+    if (rcs[g]) return fail(rcs[g], "device %d: %s", devs[g], msgs[g].c_str());
+  return 0;
+}
+
+// dt = 1.0/(2.0*(maximum(D)/(dr^2) + sum(k)/4))*0.99 on dual numbers (basepdesolver.jl:696): value and, in slot 29 of
+// every seed row, its partial along that direction (sum rule over k, the partial of the largest D, quotient rule)
+int gab1_default_dt_tangent(int64_t S, int32_t n_dir, const double* D, const double* k, double dr, double* dt, double* seeds) {
+  if (!D || !k || !dt || !seeds || n_dir < 1) return fail(-2, "bad arguments to gab1_default_dt_tangent");
+  for (int64_t i = 0; i < S; ++i) {
+    int im = 0;
+    for (int q = 1; q < GAB1_N_D; ++q) if (D[i * GAB1_N_D + q] > D[i * GAB1_N_D + im]) im = q;
+    double sk = 0.0;
+    for (int q = 0; q < GAB1_N_K; ++q) sk += k[i * GAB1_N_K + q];
+    const double den = 2.0 * (D[i * GAB1_N_D + im] / (dr * dr) + sk / 4);
+    const double inv = 1.0 / den;
+    dt[i] = inv * 0.99;
+    for (int d = 0; d < n_dir; ++d) {
+      double* s = seeds + (i * n_dir + d) * GAB1_N_SEED;
+      double dsk = 0.0;
+      for (int q = 0; q < GAB1_N_K; ++q) dsk += s[GAB1_N_D + q];
+      const double dden = 2.0 * (s[im] / (dr * dr) + dsk / 4);
+      s[GAB1_N_SEED - 1] = (-(inv / den) * dden) * 0.99;
+    }
+  }
+  return 0;
 }
 
 void gab1_release_device_memory(void) {

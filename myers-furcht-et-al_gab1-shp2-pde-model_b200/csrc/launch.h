@@ -47,6 +47,15 @@ size_t quantiles_workspace_bytes(long long S);
 int ensemble_quantiles_device(const gab1_opts* o, int device, cudaStream_t stream, long long S, const double* out,
                               const int* status, unsigned matrices, int c0, int c1, int np, const double* p, double* q,
                               long long* n_valid, void* workspace);
+// forward-mode kernels (tangent_kernel.cuh): K nodes per lane, NT directions per work item
+struct TangentArgs {
+  KernelArgs a;          // a.out_stride = doubles per component block; a.out holds (1 + n_dir) blocks per set
+  const double* seeds;   // S x n_dir x GAB1_N_SEED: partials of [D(7); k(17); Co(5); dt] along each direction
+  int n_dir;
+  int groups;            // work items per set = ceil(n_dir / NT)
+};
+int tangent_directions_per_item(int K, int n_dir);
+int launch_tangent_kernel(int K, int NT, const TangentArgs& ta, int device, cudaStream_t stream);
 // diagnostics (kernels_single.cu)
 void launch_recip_error_kernel(double lo, double hi, int n, double* out);
 

@@ -51,6 +51,36 @@ class BatchResult:
         return self.out[:, off:off + o.Nts + 1]
 
 
+@dataclass
+class TangentResult:
+    """Values and forward-mode partials of a batch: out[:, 0] is what the primal call returns, out[:, 1 + d] the
+    partials of every output along seed direction d (same layout)."""
+    opts: abi.Opts
+    out: np.ndarray          # (S, 1 + n_dir, doubles_per_set)
+    status: np.ndarray
+    n_saved: np.ndarray
+    n_steps: np.ndarray
+    n_bc_iters: np.ndarray
+    r: np.ndarray
+    dt: np.ndarray           # (S,)
+    seeds: np.ndarray        # (S, n_dir, 30) as used (slot 29 = partial of dt)
+
+    def matrix(self, name: str) -> np.ndarray:
+        """(S, 1 + n_dir, Nr+1, Nts+1)"""
+        o = self.opts
+        off = abi.full_matrix_offset(o, abi.MATRIX_NAMES.index(name))
+        if off < 0:
+            raise KeyError(f"{name} was masked out")
+        P, Cn = o.Nr + 1, o.Nts + 1
+        return self.out[:, :, off:off + P * Cn].reshape(self.out.shape[0], -1, Cn, P).transpose(0, 1, 3, 2)
+
+    def vector(self, name: str) -> np.ndarray:
+        """(S, 1 + n_dir, Nts+1)"""
+        o = self.opts
+        off = abi.full_vector_offset(o, abi.VECTOR_NAMES.index(name))
+        return self.out[:, :, off:off + o.Nts + 1]
+
+
 def _grid(R, dr, r):
     return params.julia_range(dr, R) if r is None else np.asarray(r, dtype=np.float64)
 
@@ -181,6 +211,75 @@ class Frontend:
             return SolFit(None, z, z.copy(), z.copy()), np.ones(10), np.ones(10), float(res.dt[0])
         sol = SolFit(res.matrix("aSFK")[0], res.matrix("PG1S")[0], res.matrix("G2PG1S")[0], res.vector("EG2PG1S")[0])
         return sol, res.r, res.vector("t_out")[0], float(res.dt[0])
+
+    # ------------------------------------------------------------------ forward-mode (ForwardDiff.Dual) path
+    def pdesolver_tangent_batch(self, Co, Dmat, kmat, seeds, *, R=10.0, dr=0.1, tf=5.0, Nts=100, dt=None, dt_save=None,
+                                maxiters=20, tol=1e-6, geometry=abi.GEOM_SPHERICAL, sfk_mode=abi.SFK_DIFFUSIBLE,
+                                pg1tot_form=abi.PG1TOT_VIA_STOT, matrices=None, out_mode=abi.OUT_FULL, pct_mul=1.0,
+                                pct_div=1.0, r=None) -> TangentResult:
+        """The solver on dual numbers, batched: what `pdesolver_fitting(p::Vector{<:ForwardDiff.Dual})` computes
+        (basepdesolver.jl:674-932), for S parameter sets and n_dir partials each.  seeds: (S, n_dir, 30), partials of
+        [D; k; Co; dt].  dt=None: dt and its partials are computed from D, k inside, as pdesolver_fitting does (:696);
+        a given dt is a constant unless the caller filled seed slot 29."""
+        mask = abi.MASK_ALL if matrices is None else sum(1 << abi.MATRIX_NAMES.index(m) for m in matrices)
+        o = abi.make_opts(R=R, dr=dr, tf=tf, Nts=Nts, dt_save=dt_save, maxiters=maxiters, tol=tol, geometry=geometry,
+                          sfk_mode=sfk_mode, pg1tot_form=pg1tot_form, out_mode=out_mode, matrix_mask=mask, pct_mul=pct_mul,
+                          pct_div=pct_div)
+        Dmat = np.ascontiguousarray(Dmat, dtype=np.float64).reshape(-1, abi.N_D)
+        kmat = np.ascontiguousarray(kmat, dtype=np.float64).reshape(-1, abi.N_K)
+        seeds = np.ascontiguousarray(seeds, dtype=np.float64)
+        if dt is None:
+            dtv, seeds = self.backend.default_dt_tangent(Dmat, kmat, dr, seeds)
+        else:
+            dtv = np.broadcast_to(np.asarray(dt, float), (Dmat.shape[0],)).copy()
+        rr = _grid(R, dr, r)
+        out, status, n_saved, n_steps, n_bc = self.backend.solve_tangent(o, Co, Dmat, kmat, dtv, seeds, rr)
+        return TangentResult(o, out, status, n_saved, n_steps, n_bc, rr, dtv, seeds)
+
+    def pdesolver_fitting_dual(self, p, dp, *, R=10.0, dr=0.1, tf=5.0, Nts=100, dt_save=None, maxiters=20, tol=1.0e-6):
+        """pdesolver_fitting on Dual inputs (basepdesolver.jl:674-932): p = [D; k; Co] (29,), dp (n_dir, 29) its partials.
+        Returns ((sol, dsol), r, (t_out, dt_out), (dt, ddt)); dsol fields carry a leading n_dir axis."""
+        p = np.asarray(p, float)
+        dp = np.atleast_2d(np.asarray(dp, float))
+        seeds = np.zeros((1, dp.shape[0], abi.N_SEED))
+        seeds[0, :, :29] = dp
+        res = self.pdesolver_tangent_batch(p[24:29], p[None, :7], p[None, 7:24], seeds, R=R, dr=dr, tf=tf, Nts=Nts,
+                                           dt_save=dt_save, maxiters=maxiters, tol=tol,
+                                           matrices=("aSFK", "PG1S", "G2PG1S"))
+        if res.status[0] & abi.ST_THROW:
+            z = np.zeros((10, 10))
+            return (SolFit(None, z, z.copy(), z.copy()), None), np.ones(10), (np.ones(10), None), (float(res.dt[0]), res.seeds[0, :, 29])
+        m = {n: res.matrix(n)[0] for n in ("aSFK", "PG1S", "G2PG1S")}
+        v = res.vector("EG2PG1S")[0]
+        t = res.vector("t_out")[0]
+        sol = SolFit(m["aSFK"][0], m["PG1S"][0], m["G2PG1S"][0], v[0])
+        dsol = SolFit(m["aSFK"][1:], m["PG1S"][1:], m["G2PG1S"][1:], v[1:])
+        return (sol, dsol), res.r, (t[0], t[1:]), (float(res.dt[0]), res.seeds[0, :, 29].copy())
+
+    def fitting_loss_and_gradient(self, pvals_in, mu, sigma, *, param_inds, pvals0, Co, R=10.0, dr=0.2, tf=5.0, Nts=100,
+                                  tol=1e-3, maxiters=20):
+        """`loss` of param_fitting+inference_finitediff.jl:188-226 and its ForwardDiff gradient (:238-240), for a batch of
+        points: pvals_in (S, n) are log-parameters, x2[param_inds] = exp.(pvals_in) (:201-202, 0-based indices into
+        [D; k] here), ŷ = % SHP2-bound GAB1 (:211-216), loss = (μ - ŷ)^2 / σ^2 (:219).
+        Returns (loss (S,), grad (S, n), yhat (S,)); loss = inf where the reference returns Inf (NaN)."""
+        x = np.atleast_2d(np.asarray(pvals_in, float))
+        S, n = x.shape
+        P = np.tile(np.asarray(pvals0, float), (S, 1))
+        ex = np.exp(x)
+        P[:, list(param_inds)] = ex
+        seeds = np.zeros((S, n, abi.N_SEED))
+        for i, j in enumerate(param_inds):
+            seeds[:, i, j] = ex[:, i]
+        volCF, surfCF = params.conversion_factors(R)
+        res = self.pdesolver_tangent_batch(Co, P[:, :7], P[:, 7:24], seeds, R=R, dr=dr, tf=tf, Nts=Nts, tol=tol,
+                                           maxiters=maxiters, out_mode=abi.OUT_PCT_BOUND, pct_mul=volCF, pct_div=surfCF)
+        yhat = res.out[:, 0, 0]
+        dy = res.out[:, 1:, 0]
+        loss = (mu - yhat) ** 2 / sigma ** 2
+        grad = (-2.0 * (mu - yhat) / sigma ** 2)[:, None] * dy
+        bad = np.isnan(loss)
+        loss = np.where(bad, np.inf, loss)
+        return loss, grad, yhat
 
     def pulsechase_solver(self, Co, D, k, *, R=10.0, dr=0.1, t_prechase=5.0, t_chase=2.0, tf=None, Nts=100, dt=None,
                           dt_save=None, maxiters=20, tol=1.0e-6):
@@ -325,5 +424,6 @@ _default = Frontend(abi.CudaBackend())
 for _n in ("pdesolver_batch", "sapdesolver_batch", "pdesolver", "pdesolver_membSFK", "pdesolver_rect",
            "pdesolver_membSFK_rect", "pdesolver_fitting", "pulsechase_solver", "sapdesolver", "sapdesolver_membSFK",
            "run_ensemble", "run_ensemble_pc", "pmap_fun_dk", "pmap_fun_allpars", "pmap_fun_dk_combD", "pmap_fun_concs",
-           "fbatch_dk_mt", "fbatch_concs_mt", "pct_shp2_bound_gab1"):
+           "fbatch_dk_mt", "fbatch_concs_mt", "pct_shp2_bound_gab1", "pdesolver_tangent_batch", "pdesolver_fitting_dual",
+           "fitting_loss_and_gradient"):
     globals()[_n] = getattr(_default, _n)

@@ -18,12 +18,16 @@ pkg = importlib.import_module("myers-furcht-et-al_gab1-shp2-pde-model_b200")
 abi = pkg.abi
 
 _lib = None
+_dual = None
+LIB_DUAL = HERE / "libgab1_oracle_dual.so"
 
 
 def build(force: bool = False) -> Path:
     src = HERE / "gab1_oracle.c"
     hdr = HERE.parent / "include" / "gab1pde.h"
-    if force or not LIB.exists() or LIB.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime):
+    src2 = HERE / "gab1_oracle_dual.cpp"
+    if force or not LIB.exists() or LIB.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime) or \
+            not LIB_DUAL.exists() or LIB_DUAL.stat().st_mtime < max(src2.stat().st_mtime, hdr.stat().st_mtime):
         subprocess.run(["make", "-C", str(HERE), "-B"], check=True, capture_output=True)
     return LIB
 
@@ -40,6 +44,21 @@ def load():
         lib.gab1o_out_doubles_per_set.restype = C.c_int64
         _lib = lib
     return _lib
+
+
+def load_dual():
+    """The forward-mode (dual-number) restatement, oracle/gab1_oracle_dual.cpp."""
+    global _dual
+    if _dual is None:
+        build()
+        lib = C.CDLL(str(LIB_DUAL))
+        lib.gab1o_solve_tangent.argtypes = abi.TANGENT_ARGTYPES + [C.c_int32]
+        lib.gab1o_solve_tangent.restype = C.c_int
+        dp = C.POINTER(C.c_double)
+        lib.gab1o_default_dt_dual.argtypes = [C.c_int64, C.c_int32, dp, dp, C.c_double, dp, dp]
+        lib.gab1o_default_dt_dual.restype = C.c_int
+        _dual = lib
+    return _dual
 
 
 def max_threads() -> int:
@@ -60,6 +79,17 @@ class OracleBackend:
             raise RuntimeError(f"oracle rejected the options ({rc})")
         return out, status, n_saved, n_steps, n_bc
 
+
+    def solve_tangent(self, o, Co, D, k, dt, seeds, r):
+        lib = load_dual()
+        rc, out, status, n_saved, n_steps, n_bc = abi.call_solve_tangent(lib.gab1o_solve_tangent, o, Co, D, k, dt, seeds, r,
+                                                                         C.c_int32(self.nthreads))
+        if rc != 0:
+            raise RuntimeError(f"dual oracle rejected the options ({rc})")
+        return out, status, n_saved, n_steps, n_bc
+
+    def default_dt_tangent(self, D, k, dr, seeds):
+        return abi._default_dt_tangent(load_dual().gab1o_default_dt_dual, D, k, dr, seeds)
 
     def solve_quantiles(self, o, Co, D, k, dt, r, matrices, c0, c1, probs):
         """CPU restatement of gab1_solve_ensemble_quantiles: the oracle's FULL result, NaN sets dropped, then the order
