@@ -163,7 +163,7 @@ function pdesolver_membSFK_rect(Co::Vector{Float64}, D::Vector{Float64}, k::Vect
     _check(b); nc = Int(b.n_saved[1])
     _sol(b, 1; extra=true, ncol=nc), b.r, vector(b, :t_out, 1)[1:nc], dt
 end
-"Float64 path of pdesolver_fitting (basepdesolver.jl:674-932); the ForwardDiff.Dual path stays on the reference code"
+"Float64 path of pdesolver_fitting (basepdesolver.jl:674-932); the ForwardDiff.Dual method is below (solve_tangent)"
 function pdesolver_fitting(p::AbstractVector{Float64}; Diff_inds=1:7, k_inds=Diff_inds[end] .+ (1:17),
                            Co_inds=k_inds[end] .+ (1:5), R=10.0, dr=0.1, tf=5.0, Nts=100, dt_save=tf / Nts,
                            maxiters=20, tol=1.0e-6)
@@ -177,6 +177,57 @@ function pdesolver_fitting(p::AbstractVector{Float64}; Diff_inds=1:7, k_inds=Dif
     (aSFK=matrix(b, :aSFK, 1), PG1S=matrix(b, :PG1S, 1), G2PG1S=matrix(b, :G2PG1S, 1), EG2PG1S=vector(b, :EG2PG1S, 1)),
     b.r, vector(b, :t_out, 1), dt
 end
+## ---------------------------------------------------------------- forward mode: pdesolver_fitting on ForwardDiff duals
+# ForwardDiff.gradient(testf, x) / AutoForwardDiff() / Turing NUTS call pdesolver_fitting with eltype(p) <: Dual
+# (param_fitting+inference_finitediff.jl:128-151,188-240,308-370).  This method peels values and partials off the duals,
+# lets the library propagate the partials through the whole time loop (gab1_solve_tangent), and re-wraps the outputs as
+# duals with the caller's tag, so the calling code (loss, testf, turing_model) runs unchanged.
+using ForwardDiff: Dual, Partials, value, partials
+
+"values + partials of S sets: seeds is 30 × n_dir × S ([D;k;Co;dt] partials); returns out (n, 1+n_dir, S) and diagnostics"
+function solve_tangent(o::Opts, Co, Dmat, kmat, dt::Vector{Float64}, seeds::Array{Float64,3}, r::Vector{Float64})
+    S = size(Dmat, 1); n_dir = size(seeds, 2)
+    Dt = permutedims(Float64.(Dmat)); kt = permutedims(Float64.(kmat))
+    Cot, stride = Co isa AbstractVector ? (Float64.(Co), 0) : (permutedims(Float64.(Co)), 5)
+    n = out_doubles(o)
+    out = zeros(Float64, n, 1 + n_dir, S); status = zeros(Int32, S); n_saved = zeros(Int32, S)
+    n_steps = zeros(Int64, S); n_bc = zeros(Int64, S)
+    rc = ccall((:gab1_solve_tangent, LIB), Cint,
+               (Ref{Opts}, Int64, Int32, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}),
+               o, S, n_dir, Cot, stride, Dt, kt, dt, seeds, r, out, status, n_saved, n_steps, n_bc)
+    rc == 0 || error("gab1_solve_tangent: " * unsafe_string(ccall((:gab1_last_error, LIB), Cstring, ())))
+    out, status, n_saved, n_steps, n_bc
+end
+
+function pdesolver_fitting(p::AbstractVector{Dual{Tg,Float64,N}}; Diff_inds=1:7, k_inds=Diff_inds[end] .+ (1:17),
+                           Co_inds=k_inds[end] .+ (1:5), R=10.0, dr=0.1, tf=5.0, Nts=100, dt_save=tf / Nts,
+                           maxiters=20, tol=1.0e-6) where {Tg,N}
+    D, k, Co = p[Diff_inds], p[k_inds], p[Co_inds]
+    dt = 1.0 / (2.0 * (maximum(D) / (dr .^ 2) + sum(k) / 4)) * 0.99          # a Dual, as at basepdesolver.jl:696
+    seeds = zeros(Float64, 30, N, 1)
+    for d in 1:N
+        seeds[1:7, d, 1] = [partials(x, d) for x in D]
+        seeds[8:24, d, 1] = [partials(x, d) for x in k]
+        seeds[25:29, d, 1] = [partials(x, d) for x in Co]
+        seeds[30, d, 1] = partials(dt, d)
+    end
+    o = make_opts(; R, dr, tf, Nts, dt_save, maxiters, tol, matrix_mask=UInt32((1 << 1) | (1 << 9) | (1 << 7)))
+    r = collect(0.0:dr:R)
+    out, status, = solve_tangent(o, value.(Co), reshape(value.(D), 1, :), reshape(value.(k), 1, :), [value(dt)], seeds, r)
+    if status[1] & ST_THROW != 0
+        z() = zeros(eltype(p), 10, 10)
+        return (PG1S=z(), G2PG1S=z(), EG2PG1S=z()), ones(10), ones(10), dt
+    end
+    P, C = o.Nr + 1, o.Nts + 1
+    dual(i) = Dual{Tg}(out[i, 1, 1], Partials(ntuple(d -> out[i, 1 + d, 1], N)))
+    mat(name) = (off = ccall((:gab1_full_matrix_offset, LIB), Int64, (Ref{Opts}, Int32), o, findfirst(==(name), MATRICES) - 1);
+                 reshape([dual(off + i) for i in 1:P*C], P, C))
+    vec(name) = (off = ccall((:gab1_full_vector_offset, LIB), Int64, (Ref{Opts}, Int32), o, findfirst(==(name), VECTORS) - 1);
+                 [dual(off + i) for i in 1:C])
+    (aSFK=mat(:aSFK), PG1S=mat(:PG1S), G2PG1S=mat(:G2PG1S), EG2PG1S=vec(:EG2PG1S)), r, vec(:t_out), dt
+end
+
 "pulsechase_solver (pulsechase_solver.jl:29-318)"
 function pulsechase_solver(Co::AbstractVector, D::AbstractVector, k::AbstractVector; R=10.0, dr=0.1, t_prechase=5.0,
                            t_chase=2.0, tf=t_prechase + t_chase, Nts=100, dt=default_dt(D, k, dr), dt_save=tf / Nts,

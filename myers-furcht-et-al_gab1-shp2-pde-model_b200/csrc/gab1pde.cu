@@ -235,7 +235,7 @@ int solve_tangent_device(const gab1_opts* o, int device, cudaStream_t stream, lo
   int NT = gab1::tangent_directions_per_item(K, n_dir);
   if (const char* e = getenv("GAB1_TANGENT_NT")) {      // A/B measurements
     const int v = atoi(e);
-    if ((v == 1) || (v == 2 && K <= 2) || (v == 4 && K == 1)) NT = v;
+    if ((v == 1) || (v == 2 && K <= 4) || (v == 4 && K <= 2)) NT = v;
   }
   ta.groups = (n_dir + NT - 1) / NT;
   CUDA_TRY(cudaMemsetAsync(w.counter, 0, sizeof(unsigned), stream));

@@ -56,6 +56,8 @@ int launch_tangent_kernel(int K, int NT, const TangentArgs& ta, int device, cuda
     case 14: return launch<1, 4>(ta, device, stream);
     case 21: return launch<2, 1>(ta, device, stream);
     case 22: return launch<2, 2>(ta, device, stream);
+    case 24: return launch<2, 4>(ta, device, stream);
+    case 42: return launch<4, 2>(ta, device, stream);
     case 41: return launch<4, 1>(ta, device, stream);
   }
   return fail(-6, "no tangent kernel for K=%d, NT=%d", K, NT);

@@ -4,8 +4,12 @@
 Bars:
   * value block: as the primal fast kernels — |gpu - ref| <= 1e-9 * max(|ref|, 1e-6 * max|field|), identical step counts,
     snapshot schedules, membrane-iteration counts and status words;
-  * partials: |gpu - ref| <= TTOL * max|ref| over the same output array (matrix / vector / profile) of the same set and
-    direction, TTOL = 1e-9.  (A partial changes sign inside an array, so an element-wise relative bound is meaningless.)
+  * partials: |gpu - ref| <= TTOL * scale, TTOL = 1e-9, where scale is taken over the same output array (matrix / vector /
+    profile) of the same set and direction: scale = max(max|ref partial|, 1e-6 * max|ref value| * max_i |seed_i / p_i|).
+    A partial changes sign inside an array, so an element-wise relative bound is meaningless; and a partial that is a
+    million times smaller than the array's values per unit RELATIVE change of the parameter (e.g. d GAB1 / d D_S = 1e-13
+    with membrane SFKs) is the residue of a cancellation, defined only to ~1e-16 * |value| in either implementation — the
+    second term is the same 1e-6 floor the value bound uses.
 """
 import os
 
@@ -57,28 +61,45 @@ def value_err(a, b):
         return float(np.where(fin & (den > 0), np.abs(a - b) / den, 0.0).max())
 
 
-def tangent_err(res, ref, abi):
+def rel_seed(res, Co, D, k):
+    """max_i |seed_i / p_i| per (set, direction): the relative size of the parameter perturbation a unit step along the
+    direction makes."""
+    S = D.shape[0]
+    p = np.concatenate([D, k, np.broadcast_to(Co, (S, 5)), res.dt[:, None]], axis=1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        q = np.where(res.seeds != 0, np.abs(res.seeds / p[:, None, :]), 0.0)
+    return q.max(axis=-1)[:, :, None]
+
+
+def tangent_err(res, ref, abi, rs=None):
     worst = 0.0
     for lo, hi in blocks(res.opts, abi):
         a, b = res.out[:, 1:, lo:hi], ref.out[:, 1:, lo:hi]
         assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN pattern of the partials differs"
         fin = np.isfinite(b)
         scale = np.where(fin, np.abs(b), 0).max(axis=-1, keepdims=True)
+        if rs is not None:
+            v = ref.out[:, :1, lo:hi]
+            vmax = np.where(np.isfinite(v), np.abs(v), 0).max(axis=-1, keepdims=True)
+            scale = np.maximum(scale, 1e-6 * vmax * rs)
         with np.errstate(invalid="ignore", divide="ignore"):
             e = np.where(fin & (scale > 0), np.abs(a - b) / scale, np.where(fin, np.abs(a - b), 0.0))
         worst = max(worst, float(e.max()))
     return worst
 
 
-def check(res, ref, abi):
+def check(res, ref, abi, pars=None):
     np.testing.assert_array_equal(res.n_steps, ref.n_steps)
     np.testing.assert_array_equal(res.n_saved, ref.n_saved)
-    np.testing.assert_array_equal(res.n_bc_iters, ref.n_bc_iters)
+    # a diverging set's iteration count during the blow-up is not reproducible between contracted and strict arithmetic
+    # (the primal fast kernels are held to the same rule, test_gpu_parity.py): compare the counts of the healthy sets
+    good = (ref.status & abi.ST_NAN) == 0
+    np.testing.assert_array_equal(res.n_bc_iters[good], ref.n_bc_iters[good])
     np.testing.assert_array_equal(res.status, ref.status)
     ev = value_err(res.out[:, 0], ref.out[:, 0])
-    et = tangent_err(res, ref, abi)
+    et = tangent_err(res, ref, abi, None if pars is None else rel_seed(res, *pars))
     assert ev < RTOL, f"value block: relative error {ev:.3e}"
-    assert et < TTOL, f"partials: error {et:.3e} of the array maximum"
+    assert et < TTOL, f"partials: error {et:.3e} of the array scale"
     return ev, et
 
 
@@ -102,7 +123,7 @@ def test_tangents_match_the_dual_oracle(pkg, gfe, ofe, ensemble, grid, mode):
     ref = ofe.pdesolver_tangent_batch(Co, D, k, seeds, **kw)
     np.testing.assert_array_equal(res.seeds, ref.seeds)
     np.testing.assert_array_equal(res.dt, ref.dt)
-    check(res, ref, abi)
+    check(res, ref, abi, (Co, D, k))
 
 
 @pytest.mark.parametrize("nt", ["1", "2", "4"])
@@ -117,11 +138,11 @@ def test_direction_grouping(pkg, gfe, ofe, ensemble, nt, n_dir, monkeypatch):
     cols = [1, 7 + 8, 24 + 2, 7 + 1, 24 + 4][:n_dir]
     rng = np.random.default_rng(5)
     seeds = unit_seeds(7, cols) + (rng.standard_normal((7, n_dir, 30)) * 1e-3 if n_dir == 5 else 0.0)   # dense directions too
-    for grid in ("K1", "K2") if nt != "4" else ("K1",):
+    for grid in ("K1", "K2", "K4") if nt == "2" else ("K1", "K2"):
         kw = dict(tol=1e-4, maxiters=20, **GRIDS[grid])
         res = gfe.pdesolver_tangent_batch(Co, D, k, seeds, **kw)
         ref = ofe.pdesolver_tangent_batch(Co, D, k, seeds, **kw)
-        check(res, ref, abi)
+        check(res, ref, abi, (Co, D, k))
 
 
 @pytest.mark.parametrize("variant", [dict(geometry=1, pg1tot_form=1), dict(sfk_mode=1), dict(geometry=1, sfk_mode=2, pg1tot_form=1)])
@@ -134,7 +155,7 @@ def test_variants(pkg, gfe, ofe, ensemble, variant):
     kw = dict(tol=1e-4, maxiters=20, dr=0.2, tf=0.1, Nts=4, **variant)
     res = gfe.pdesolver_tangent_batch(Co, D, k, seeds, **kw)
     ref = ofe.pdesolver_tangent_batch(Co, D, k, seeds, **kw)
-    check(res, ref, abi)
+    check(res, ref, abi, (Co, D, k))
 
 
 def test_value_block_equals_the_primal_kernel_schedule(pkg, gfe, ensemble):
@@ -163,19 +184,21 @@ def test_diverging_set_and_edge_cases(pkg, gfe, ofe, ensemble):
     res = gfe.pdesolver_tangent_batch(Co, D, k, seeds, dt=dt, **kw)
     ref = ofe.pdesolver_tangent_batch(Co, D, k, seeds, dt=dt, **kw)
     assert res.status[0] & abi.ST_NAN and res.status[2] & abi.ST_THROW
-    check(res, ref, abi)
+    check(res, ref, abi, (Co, D, k))
+    pri = gfe.pdesolver_batch(Co, D, k, dt=dt, **kw)               # the diverging set: same control flow as the primal kernel
+    np.testing.assert_array_equal(res.n_bc_iters, pri.n_bc_iters)
     # more snapshots due than columns (dt_save tiny)
     kw2 = dict(dr=0.5, tf=0.2, Nts=3, dt_save=0.01, tol=1e-4, maxiters=20)
     res = gfe.pdesolver_tangent_batch(Co, D[1:2], k[1:2], seeds[1:2], **kw2)
     ref = ofe.pdesolver_tangent_batch(Co, D[1:2], k[1:2], seeds[1:2], **kw2)
     assert res.status[0] & abi.ST_OVERFLOW
-    check(res, ref, abi)
+    check(res, ref, abi, (Co, D, k))
     # fewer snapshots than columns
     kw3 = dict(dr=0.5, tf=0.2, Nts=3, dt_save=0.15, tol=1e-4, maxiters=20)
     res = gfe.pdesolver_tangent_batch(Co, D[1:2], k[1:2], seeds[1:2], **kw3)
     ref = ofe.pdesolver_tangent_batch(Co, D[1:2], k[1:2], seeds[1:2], **kw3)
     assert res.status[0] & abi.ST_SHORT
-    check(res, ref, abi)
+    check(res, ref, abi, (Co, D, k))
     empty = gfe.pdesolver_tangent_batch(Co, D[:0], k[:0], seeds[:0], dr=0.5, tf=0.1, Nts=2)
     assert empty.out.shape[0] == 0
 
