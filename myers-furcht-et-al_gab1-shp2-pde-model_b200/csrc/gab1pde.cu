@@ -232,10 +232,21 @@ int solve_tangent_device(const gab1_opts* o, int device, cudaStream_t stream, lo
   a.P_pad = (o->Nr + 1 + 3) & ~3;
   ta.seeds = seeds;
   ta.n_dir = n_dir;
-  int NT = gab1::tangent_directions_per_item(K, n_dir);
-  if (const char* e = getenv("GAB1_TANGENT_NT")) {      // A/B measurements
+  // Kernel choice, measured on B200 with 4 partials per set:
+  //   Nr <= 32        streamed kernel, 2 directions per item   (all five variants within 4 % of each other)
+  //   32 < Nr <= 64   register kernel, 2 directions per item   (11.6x a primal solve; streamed with 4: 15.7x)
+  //   64 < Nr <= 128  streamed kernel, 4 directions per item   (16.2x; register kernel with 1: 26.8x)
+  //   one direction   register kernel
+  // GAB1_TANGENT = reg | stream and GAB1_TANGENT_NT = 1 | 2 | 4 override for A/B measurements.
+  bool streamed = n_dir >= 2 && K != 2;
+  int NT = n_dir == 1 ? 1 : (K == 4 && n_dir >= 3 ? 4 : 2);
+  if (const char* e = getenv("GAB1_TANGENT")) {
+    if (strcmp(e, "reg") == 0) { streamed = false; NT = gab1::tangent_directions_per_item(K, n_dir); }
+    if (strcmp(e, "stream") == 0) { streamed = true; NT = n_dir >= 3 ? 4 : 2; }
+  }
+  if (const char* e = getenv("GAB1_TANGENT_NT")) {
     const int v = atoi(e);
-    if ((v == 1) || (v == 2 && K <= 4) || (v == 4 && K <= 2)) NT = v;
+    if (streamed ? (v == 2 || v == 4) : ((v == 1) || (v == 2 && K <= 2) || (v == 4 && K == 1))) NT = v;
   }
   ta.groups = (n_dir + NT - 1) / NT;
   CUDA_TRY(cudaMemsetAsync(w.counter, 0, sizeof(unsigned), stream));
@@ -247,7 +258,8 @@ int solve_tangent_device(const gab1_opts* o, int device, cudaStream_t stream, lo
   size_t bytes = w.cub_bytes;
   CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp, bytes, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)S,
                                                      0, 32, stream));
-  return gab1::launch_tangent_kernel(K, NT, ta, device, stream);
+  return streamed ? gab1::launch_tangent_stream_kernel(K, NT, ta, device, stream)
+                  : gab1::launch_tangent_kernel(K, NT, ta, device, stream);
 }
 
 // ---- FP64 peak: register-resident DFMA chains ------------------------------------------------------------------

@@ -56,6 +56,8 @@ struct TangentArgs {
 };
 int tangent_directions_per_item(int K, int n_dir);
 int launch_tangent_kernel(int K, int NT, const TangentArgs& ta, int device, cudaStream_t stream);
+// streamed-partials kernels (tangent_stream_kernel.cuh): primal in registers, partials in shared memory; NT in {2, 4}
+int launch_tangent_stream_kernel(int K, int NT, const TangentArgs& ta, int device, cudaStream_t stream);
 // diagnostics (kernels_single.cu)
 void launch_recip_error_kernel(double lo, double hi, int n, double* out);
 
