@@ -143,7 +143,7 @@ int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long 
   if (Co_stride != 0 && Co_stride != GAB1_N_CO) return fail(-2, "Co_stride must be 0 or 5");
   if (!Co || !D || !k || !dt || !r || !out || !workspace) return fail(-2, "a required buffer is NULL");
   const int K = pick_K(o->Nr);
-  if (K == 0) return fail(-6, "Nr = %d: grids with more than 256 nodes are not supported by this build", o->Nr);
+  if (o->Nr > 512) return fail(-6, "Nr = %d: grids with more than 512 nodes are not supported by this build", o->Nr);
   CUDA_TRY(cudaSetDevice(device));
 
   Workspace w;
@@ -177,6 +177,19 @@ int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long 
   const bool degenerate = o->bc_loop == GAB1_BC_FOR_BREAK && o->maxiters == 0;
   const int mode = (o->arith == 1 || degenerate) ? gab1::MODE_STRICT
                    : (o->bc_loop == GAB1_BC_WHILE ? gab1::MODE_FAST_WHILE : gab1::MODE_FAST_FOR);
+  if (mode == gab1::MODE_STRICT && K == 0)
+    return fail(-6, "Nr = %d: the strict kernels (arith = 1, maxiters = 0) hold at most 256 nodes", o->Nr);
+  // ---- large grids: the state lives in shared memory (stream_kernel.cuh).  Measured on B200:
+  //      Nr = 200, 1184 sets: 1667 ms against 2808 ms for the register-resident K = 8 kernel (which spills its state);
+  //      Nr = 100: 416 vs 392 ms, Nr = 50: 191 vs 117 ms — the register kernels keep the small grids.
+  //      GAB1_KERNEL=stream forces this family for Nr > 32 (A/B measurements, parity tests).
+  if (mode != gab1::MODE_STRICT) {
+    const char* e = getenv("GAB1_KERNEL");
+    const bool forced = e && strcmp(e, "stream") == 0 && o->Nr > 32;
+    const bool other = e && e[0] && strcmp(e, "stream") != 0 && o->Nr <= 256;     // an explicit request for another family
+    if (forced || (o->Nr > 128 && !other))
+      return gab1::launch_stream_kernel(o->Nr <= 64 ? 2 : (o->Nr <= 128 ? 4 : (o->Nr <= 256 ? 8 : 16)), mode, a, device, stream);
+  }
   // ---- fast arithmetic: the skewed kernels of pair_kernel.cuh ----
   const FastPick fp = mode != gab1::MODE_STRICT ? pick_fast(o->Nr) : FastPick{0, 0, 0};
   if (fp.K) {

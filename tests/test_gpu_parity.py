@@ -292,6 +292,8 @@ FAMILIES = {
     "group32": [0.2, 0.1, 0.05],
     "group32p": [0.2],
     "group32t": [0.2],
+    # state in shared memory (stream_kernel.cuh): K = 4, 8, 16 nodes per lane; dr = 0.025 (Nr = 400) exists only here
+    "stream": [0.2, 0.1, 0.05, 0.025],
 }
 
 
@@ -306,7 +308,7 @@ def test_every_kernel_family_matches_the_oracle(pkg, gfe, ofe, ensemble, family,
     Co = pkg.params.base_Co()
     rows = [0, 1, 2, 3, 4, 2500, 4999]
     for dr in FAMILIES[family]:
-        tf = {0.4: 0.6, 0.25: 0.5, 0.2: 0.5, 0.1: 0.15, 0.05: 0.04}[dr]
+        tf = {0.4: 0.6, 0.25: 0.5, 0.2: 0.5, 0.1: 0.15, 0.05: 0.04, 0.025: 0.01}[dr]
         for variant in ("pdesolver", "rect", "pulsechase", "membSFK"):
             kw = dict(dr=dr, tf=tf, Nts=7, tol=1e-4, maxiters=20, **VARIANTS[variant])
             res = gfe.pdesolver_batch(Co, ensemble[rows, :7], ensemble[rows, 7:], **kw)
@@ -329,3 +331,34 @@ def test_every_kernel_family_matches_the_oracle(pkg, gfe, ofe, ensemble, family,
                 assert rel_err(res.out[:, 4:], ref.out[:, 4:]) < RTOL
             else:
                 assert rel_err(res.out, ref.out) < RTOL
+
+
+def test_finest_grid_all_outputs_and_edge_cases(pkg, gfe, ofe, ensemble):
+    """dr = 0.025 (Nr = 400, the reference's finest grid: SURVEY §8a4 stretch) runs on the shared-memory-resident kernel with
+    16 nodes per lane; Nr = 250 (length_scale_estimates.jl: R = 100, dr = 0.4) with 8.  FINAL_STATE, PCT_BOUND, per-set Co,
+    ragged dt, snapshot overflow, unusable dt, a grid too large for the build."""
+    abi = pkg.abi
+    rows = [0, 1, 2, 4999, 75]
+    D, k = ensemble[rows, :7], ensemble[rows, 7:]
+    Co = np.tile(pkg.params.base_Co(), (5, 1)) * np.array([[1.0], [0.5], [2.0], [1.0], [1.0]])
+    volCF, surfCF = pkg.params.conversion_factors()
+    for dr, R, tf in ((0.025, 10.0, 0.004), (0.4, 100.0, 0.6)):
+        dt = pkg.params.default_dt(D, k, dr) * np.array([1.0, 0.9, 0.8, 1.0, 0.0])       # the last set: Int64(ceil(tf/0)) throws
+        for om in (abi.OUT_FINAL_STATE, abi.OUT_PCT_BOUND, abi.OUT_FULL):
+            kw = dict(R=R, dr=dr, tf=tf, Nts=4, dt=dt, tol=1e-4, maxiters=20, out_mode=om, pct_mul=volCF, pct_div=surfCF)
+            res = gfe.pdesolver_batch(Co, D, k, **kw)
+            ref = ofe.pdesolver_batch(Co, D, k, **kw)
+            check_control_flow(res, ref)
+            assert res.status[4] & abi.ST_THROW
+            assert rel_err(res.out, ref.out) < RTOL
+    kw = dict(dr=0.025, tf=0.004, Nts=3, dt_save=0.0002, tol=1e-4, maxiters=20)
+    res = gfe.pdesolver_batch(Co[:2], D[:2], k[:2], **kw)
+    ref = ofe.pdesolver_batch(Co[:2], D[:2], k[:2], **kw)
+    assert np.all(res.status & abi.ST_OVERFLOW)
+    check_control_flow(res, ref)
+    assert rel_err(res.out, ref.out) < RTOL
+    with pytest.raises(abi.Gab1Error, match="512"):
+        gfe.pdesolver_batch(Co[:1], D[:1], k[:1], dr=0.01, tf=1e-5, Nts=2)
+    strict = pkg.host.Frontend(abi.CudaBackend(arith=abi.ARITH_STRICT))
+    with pytest.raises(abi.Gab1Error, match="strict"):
+        strict.pdesolver_batch(Co[:1], D[:1], k[:1], dr=0.025, tf=1e-5, Nts=2)
