@@ -46,8 +46,12 @@ __device__ void solve_set_streamed(const KernelArgs& a, long long set, int lane,
   double* oset = a.out + set * a.out_stride;
   unsigned status = 0;
   const unsigned ws_s = (unsigned)__cvta_generic_to_shared(ws);
-  auto u_at = [&](int q, int i) { return ws_s + 8u * (unsigned)(LY::U + (q * K + i) * 32 + lane); };
-  auto a_at = [&](int i) { return ws_s + 8u * (unsigned)(LY::A + i * 32 + lane); };
+  // The state and the grid coefficient are touched by their own lane only: plain accesses (not the volatile lds/sts of
+  // the exchange header), so that ptxas may hoist the next node's loads over this node's arithmetic and stores.
+  double* const U_ = ws + LY::U + lane;
+  double* const A_ = ws + LY::A + lane;
+  auto u_at = [&](int q, int i) -> double& { return U_[(q * K + i) * 32]; };
+  auto a_at = [&](int i) -> double& { return A_[i * 32]; };
   const int G = (Nr + K - 1) / K;                     // lanes in use; slots are right-aligned on the grid
   const int off = Nr - G * K;                         // node of (lane, i) = lane*K + i + 1 + off
 
@@ -85,13 +89,13 @@ __device__ void solve_set_streamed(const KernelArgs& a, long long set, int lane,
       const int n = lane * K + i + 1 + off;
       const bool on = n >= 1 && n <= Nr;
       const double r = on ? a.r[n] : 1.0;
-      sts(a_at(i), (a.o.geometry == GAB1_GEOM_SPHERICAL) ? 1.0 / (r * dr) : 0.0);
+      a_at(i) = (a.o.geometry == GAB1_GEOM_SPHERICAL) ? 1.0 / (r * dr) : 0.0;
 #pragma unroll
-      for (int q = 0; q < NCY; ++q) sts(u_at(q, i), 0.0);
-      sts(u_at(iSFK, i), on ? CoSFK : 0.0);          // basepdesolver.jl:137-140
-      sts(u_at(GAB1, i), on ? CoG1 : 0.0);
-      sts(u_at(GRB2, i), on ? CoG2 : 0.0);
-      sts(u_at(SHP2, i), on ? CoS2 : 0.0);
+      for (int q = 0; q < NCY; ++q) u_at(q, i) = 0.0;
+      u_at(iSFK, i) = on ? CoSFK : 0.0;          // basepdesolver.jl:137-140
+      u_at(GAB1, i) = on ? CoG1 : 0.0;
+      u_at(GRB2, i) = on ? CoG2 : 0.0;
+      u_at(SHP2, i) = on ? CoS2 : 0.0;
     }
   }
   const double inv_dr2 = 1.0 / (a.o.dr * a.o.dr);
@@ -101,13 +105,13 @@ __device__ void solve_set_streamed(const KernelArgs& a, long long set, int lane,
   constexpr int idx_i = K - 2;
 
   // output helpers: one species (or a derived profile) of the whole grid staged into a row
-  auto stage_species = [&](double* row, int q) { stage_row_s<K>(row, lane, off, Nr, [&](int i) { return lds(u_at(q, i)); }); };
+  auto stage_species = [&](double* row, int q) { stage_row_s<K>(row, lane, off, Nr, [&](int i) { return u_at(q, i); }); };
   auto stage_stot = [&](double* row) {
-    stage_row_s<K>(row, lane, off, Nr, [&](int i) { return __dadd_rn(lds(u_at(PG1S, i)), lds(u_at(G2PG1S, i))); });   // basepdesolver.jl:299
+    stage_row_s<K>(row, lane, off, Nr, [&](int i) { return __dadd_rn(u_at(PG1S, i), u_at(G2PG1S, i)); });   // basepdesolver.jl:299
   };
   auto stage_ptot = [&](double* row) {
     stage_row_s<K>(row, lane, off, Nr, [&](int i) {
-      const double g2pg1 = lds(u_at(G2PG1, i)), pg1 = lds(u_at(pGAB1, i)), pg1s = lds(u_at(PG1S, i)), g2pg1s = lds(u_at(G2PG1S, i));
+      const double g2pg1 = u_at(G2PG1, i), pg1 = u_at(pGAB1, i), pg1s = u_at(PG1S, i), g2pg1s = u_at(G2PG1S, i);
       if (a.o.pg1tot_form == GAB1_PG1TOT_VIA_STOT) return __dadd_rn(__dadd_rn(g2pg1, pg1), __dadd_rn(pg1s, g2pg1s));   // :300
       return __dadd_rn(__dadd_rn(__dadd_rn(g2pg1, pg1), pg1s), g2pg1s);                                               // basepdesolver_rect.jl:261
     });
@@ -131,7 +135,7 @@ __device__ void solve_set_streamed(const KernelArgs& a, long long set, int lane,
     if (!((mask >> GAB1_M_PG1S) & 1u)) {
       bool ns = false;
 #pragma unroll 1
-      for (int i = 0; i < K; ++i) { const int n = lane * K + i + 1 + off; ns |= (n >= 1 && n <= Nr) && isnan(lds(u_at(PG1S, i))); }
+      for (int i = 0; i < K; ++i) { const int n = lane * K + i + 1 + off; ns |= (n >= 1 && n <= Nr) && isnan(u_at(PG1S, i)); }
       pg1s_nan = __any_sync(FULL, ns);
     }
     if (pg1s_nan) status |= GAB1_ST_NAN;
@@ -254,7 +258,7 @@ __device__ void solve_set_streamed(const KernelArgs& a, long long set, int lane,
       const int n = lane * K + i + 1 + off;
       if (n >= 1 && n <= Nr) {
 #pragma unroll
-        for (int q = 0; q < NCY; ++q) all_nan &= isnan(lds(u_at(q, i)));
+        for (int q = 0; q < NCY; ++q) all_nan &= isnan(u_at(q, i));
       }
     }
     return __all_sync(FULL, all_nan);
@@ -276,9 +280,9 @@ __device__ void solve_set_streamed(const KernelArgs& a, long long set, int lane,
     {
       double left[NCY], cur[NCY], hr[NCY];
 #pragma unroll
-      for (int q = 0; q < NCY; ++q) cur[q] = lds(u_at(q, 0));
+      for (int q = 0; q < NCY; ++q) cur[q] = u_at(q, 0);
 #pragma unroll
-      for (int q = 0; q < NCY; ++q) left[q] = lds(u_at(q, K - 1));
+      for (int q = 0; q < NCY; ++q) left[q] = u_at(q, K - 1);
 #pragma unroll
       for (int q = 0; q < NCY; ++q) { left[q] = shfl_up1(left[q]); hr[q] = shfl_down1(cur[q]); }
       const int n0 = lane * K + 1 + off;
@@ -287,12 +291,12 @@ __device__ void solve_set_streamed(const KernelArgs& a, long long set, int lane,
         double right[NCY];
         if (i + 1 < K) {
 #pragma unroll
-          for (int q = 0; q < NCY; ++q) right[q] = lds(u_at(q, i + 1));
+          for (int q = 0; q < NCY; ++q) right[q] = u_at(q, i + 1);
         } else {
 #pragma unroll
           for (int q = 0; q < NCY; ++q) right[q] = hr[q];
         }
-        const double aj = lds(a_at(i));
+        const double aj = a_at(i);
         const int n = n0 + i;
         const bool interior = n >= 1 && n <= Nr - 1;
         // lap = cp*u[j+1] + cm*u[j-1] + c0*u[j]; node 1 folds its mirror u[0] = u[1] into c0; zero outside the interior
@@ -324,7 +328,7 @@ __device__ void solve_set_streamed(const KernelArgs& a, long long set, int lane,
         nw[G2PG1S] = fma(Dt_G2G1S2, lap(G2PG1S), g2pg1s + v5 + v7);
 #pragma unroll
         for (int q = 0; q < NCY; ++q) {
-          sts(u_at(q, i), nw[q]);
+          u_at(q, i) = nw[q];
           if (i == idx_i && lane == lane_i) sts(ws_s + 8 * q, nw[q]);      // u+[Nr-1] for the closure lanes
           left[q] = cur[q];
           cur[q] = right[q];
@@ -377,7 +381,7 @@ __device__ void solve_set_streamed(const KernelArgs& a, long long set, int lane,
     __syncwarp();
     if (lane == lane_b) {
 #pragma unroll
-      for (int q = 0; q < NCY; ++q) sts(u_at(q, idx_b), lds(ws_s + 8 * (16 + q)));
+      for (int q = 0; q < NCY; ++q) u_at(q, idx_b) = lds(ws_s + 8 * (16 + q));
     }
     if (unconverged || nan_exit) {
       dead = all_state_nan();
@@ -438,7 +442,7 @@ __device__ void solve_set_streamed(const KernelArgs& a, long long set, int lane,
 #pragma unroll 1
     for (int i = 0; i < K; ++i)
 #pragma unroll
-      for (int q = 0; q < NCY; ++q) sts(u_at(q, i), 0.0);
+      for (int q = 0; q < NCY; ++q) u_at(q, i) = 0.0;
 #pragma unroll
     for (int j = 0; j < NMB; ++j) m[j] = 0.0;
   }

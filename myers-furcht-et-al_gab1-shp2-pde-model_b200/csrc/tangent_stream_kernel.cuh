@@ -51,11 +51,17 @@ __device__ void solve_set_tangent_stream(const TangentArgs& ta, long long set, i
   const bool lead = group == 0;
   unsigned status = 0, scratch_status = 0;
   const unsigned ws_s = (unsigned)__cvta_generic_to_shared(ws);
-  // shared-window byte addresses
-  auto sp_at = [&](int n, int q, int i) { return ws_s + 8u * (unsigned)(LY::SP + ((n * NCY + q) * K + i) * 32 + lane); };
-  auto lv_at = [&](int q, int i) { return ws_s + 8u * (unsigned)(LY::LV + (q * K + i) * 32 + lane); };
-  auto cp_at = [&](int c, int n) { return ws_s + 8u * (unsigned)(LY::CP + c * NT + n); };
-  auto lp_at = [&](int c, int n) { return ws_s + 8u * (unsigned)(LY::LP + (c * NT + n) * 32 + lane); };
+  // The partials, this step's primal Laplacians and the coefficient partials are read and written by their own lane only
+  // (the uniform ones are written once by lane 0 behind a __syncwarp): plain accesses, not the volatile lds/sts of the
+  // exchange header, so that ptxas may hoist a node's loads over the previous node's arithmetic and stores.
+  double* const SP_ = ws + LY::SP + lane;
+  double* const LV_ = ws + LY::LV + lane;
+  double* const CP_ = ws + LY::CP;
+  double* const LP_ = ws + LY::LP + lane;
+  auto sp_at = [&](int n, int q, int i) -> double& { return SP_[((n * NCY + q) * K + i) * 32]; };
+  auto lv_at = [&](int q, int i) -> double& { return LV_[(q * K + i) * 32]; };
+  auto cp_at = [&](int c, int n) -> double& { return CP_[c * NT + n]; };
+  auto lp_at = [&](int c, int n) -> double& { return LP_[(c * NT + n) * 32]; };
 
   auto block_of = [&](int c) -> double* {
     if (c == 0) return lead ? oset : nullptr;
@@ -122,7 +128,7 @@ __device__ void solve_set_tangent_stream(const TangentArgs& ta, long long set, i
       for (int q = 0; q < NCY; ++q) {
         uv[q][i] = 0.0;
 #pragma unroll
-        for (int n = 0; n < NT; ++n) sts(sp_at(n, q, i), 0.0);
+        for (int n = 0; n < NT; ++n) sp_at(n, q, i) = 0.0;
       }
       uv[iSFK][i] = on ? CoSFK.v : 0.0;      // basepdesolver.jl:776-779
       uv[GAB1][i] = on ? CoG1.v : 0.0;
@@ -130,10 +136,10 @@ __device__ void solve_set_tangent_stream(const TangentArgs& ta, long long set, i
       uv[SHP2][i] = on ? CoS2.v : 0.0;
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
-        sts(sp_at(n, iSFK, i), on ? CoSFK.p[n] : 0.0);
-        sts(sp_at(n, GAB1, i), on ? CoG1.p[n] : 0.0);
-        sts(sp_at(n, GRB2, i), on ? CoG2.p[n] : 0.0);
-        sts(sp_at(n, SHP2, i), on ? CoS2.p[n] : 0.0);
+        sp_at(n, iSFK, i) = on ? CoSFK.p[n] : 0.0;
+        sp_at(n, GAB1, i) = on ? CoG1.p[n] : 0.0;
+        sp_at(n, GRB2, i) = on ? CoG2.p[n] : 0.0;
+        sp_at(n, SHP2, i) = on ? CoS2.p[n] : 0.0;
       }
     }
     // initial column of the FULL output, every component
@@ -175,7 +181,7 @@ __device__ void solve_set_tangent_stream(const TangentArgs& ta, long long set, i
     auto put_c = [&](int c, const T& x) { cv[c] = x.v;
       if (lane == 0) {
 #pragma unroll
-        for (int n = 0; n < NT; ++n) sts(cp_at(c, n), x.p[n]);
+        for (int n = 0; n < NT; ++n) cp_at(c, n) = x.p[n];
       } };
     put_c(C_kS2f, kd(0) * dt); put_c(C_kS2r, kd(1) * dt); put_c(C_kG1f, kd(2) * dt); put_c(C_kG1r, kd(3) * dt);
     put_c(C_kG1p, kd(6) * dt); put_c(C_kG1dp, kd(7) * dt); put_c(C_kSi, kd(9) * dt);
@@ -211,7 +217,7 @@ __device__ void solve_set_tangent_stream(const TangentArgs& ta, long long set, i
     }
     auto put_l = [&](int c, const T& x) { lv_[c] = x.v;
 #pragma unroll
-      for (int n = 0; n < NT; ++n) sts(lp_at(c, n), x.p[n]); };
+      for (int n = 0; n < NT; ++n) lp_at(c, n) = x.p[n]; };
     put_l(L_cf, kf * drD);
     put_l(L_cr, kr * drD);
     put_l(L_kft, is_flux ? kf * dt : dconst<NT>(0.0));
@@ -251,10 +257,10 @@ __device__ void solve_set_tangent_stream(const TangentArgs& ta, long long set, i
     for (int n = 0; n < NT; ++n) sts(ws_s + 8 * (TWS_HDR * (1 + n) + slot), x.p[n]); };
   auto lane_const = [&](int c) { T r; r.v = lv_[c];
 #pragma unroll
-    for (int n = 0; n < NT; ++n) r.p[n] = lds(lp_at(c, n)); return r; };
+    for (int n = 0; n < NT; ++n) r.p[n] = lp_at(c, n); return r; };
   auto warp_const = [&](int c, double v) { T r; r.v = v;
 #pragma unroll
-    for (int n = 0; n < NT; ++n) r.p[n] = lds(cp_at(c, n)); return r; };
+    for (int n = 0; n < NT; ++n) r.p[n] = cp_at(c, n); return r; };
 
   T x = dconst<NT>(0.0);
   if (lane == ML + mE) { x.v = CoEGFRv;
@@ -280,7 +286,7 @@ __device__ void solve_set_tangent_stream(const TangentArgs& ta, long long set, i
 #pragma unroll
     for (int q = 0; q < NCY; ++q)
 #pragma unroll
-      for (int i = 0; i < K; ++i) w[q][i] = lds(sp_at(n, q, i));
+      for (int i = 0; i < K; ++i) w[q][i] = sp_at(n, q, i);
   };
   auto snapshot = [&](int col) {
     double mv[NMB];
@@ -316,7 +322,7 @@ __device__ void solve_set_tangent_stream(const TangentArgs& ta, long long set, i
       for (int n = 0; n < NT; ++n) {
         double mp[NMB];
         gather_m(1 + n, mp);
-        stage_row<K>(rowA, lane, g, Nr, [&](int i) { return lds(sp_at(n, PG1S, i)) + lds(sp_at(n, G2PG1S, i)); });
+        stage_row<K>(rowA, lane, g, Nr, [&](int i) { return sp_at(n, PG1S, i) + sp_at(n, G2PG1S, i); });
         pct_ave.p[n] = trapz_r2(a.r, rowA, P);
         pct_memb.p[n] = mp[EG2PG1S];
         __syncwarp();
@@ -335,7 +341,7 @@ __device__ void solve_set_tangent_stream(const TangentArgs& ta, long long set, i
 #pragma unroll
         for (int i = 0; i < K; ++i) {
           const double um = i > 0 ? uv[q][i - 1] : hl[q], upn = i + 1 < K ? uv[q][i + 1] : hr[q];
-          sts(lv_at(q, i), fma(g.cp[i], upn, fma(g.cm[i], um, g.c0[i] * uv[q][i])));
+          lv_at(q, i) = fma(g.cp[i], upn, fma(g.cm[i], um, g.c0[i] * uv[q][i]));
         }
       }
     }
@@ -344,12 +350,12 @@ __device__ void solve_set_tangent_stream(const TangentArgs& ta, long long set, i
     for (int n = 0; n < NT; ++n) {
       double cp_[C_DG2G1S2 + 1];
 #pragma unroll
-      for (int c = 0; c <= C_DG2G1S2; ++c) cp_[c] = lds(cp_at(c, n));
+      for (int c = 0; c <= C_DG2G1S2; ++c) cp_[c] = cp_at(c, n);
       double left[NCY], cur[NCY], hr[NCY];
 #pragma unroll
-      for (int q = 0; q < NCY; ++q) cur[q] = lds(sp_at(n, q, 0));
+      for (int q = 0; q < NCY; ++q) cur[q] = sp_at(n, q, 0);
 #pragma unroll
-      for (int q = 0; q < NCY; ++q) left[q] = K > 1 ? lds(sp_at(n, q, K - 1)) : cur[q];
+      for (int q = 0; q < NCY; ++q) left[q] = K > 1 ? sp_at(n, q, K - 1) : cur[q];
 #pragma unroll
       for (int q = 0; q < NCY; ++q) { left[q] = shfl_up1(left[q]); hr[q] = shfl_down1(cur[q]); }
 #pragma unroll
@@ -357,9 +363,9 @@ __device__ void solve_set_tangent_stream(const TangentArgs& ta, long long set, i
         // every load of this node first (they are in flight while the fluxes are formed), every store last
         double right[NCY], Lv[NCY];
 #pragma unroll
-        for (int q = 0; q < NCY; ++q) right[q] = i + 1 < K ? lds(sp_at(n, q, i + 1)) : hr[q];
+        for (int q = 0; q < NCY; ++q) right[q] = i + 1 < K ? sp_at(n, q, i + 1) : hr[q];
 #pragma unroll
-        for (int q = 0; q < NCY; ++q) Lv[q] = lds(lv_at(q, i));
+        for (int q = 0; q < NCY; ++q) Lv[q] = lv_at(q, i);
         const double Sa = uv[aSFK][i], G1 = uv[GAB1][i], pG1 = uv[pGAB1][i], G2 = uv[GRB2][i], g2g1 = uv[G2G1][i],
                      g2pg1 = uv[G2PG1][i], S2 = uv[SHP2][i], pg1s = uv[PG1S][i], g2pg1s = uv[G2PG1S][i];
         const double gbv = cv[C_kG1f] * G2, phv = cv[C_kG1p] * Sa, sbv = cv[C_kS2f] * S2;
@@ -399,7 +405,7 @@ __device__ void solve_set_tangent_stream(const TangentArgs& ta, long long set, i
         }
 #pragma unroll
         for (int q = 0; q < NCY; ++q) {
-          sts(sp_at(n, q, i), kin[q]);
+          sp_at(n, q, i) = kin[q];
           if (i == idx_i && lane == lane_i) sts(ws_s + 8 * (TWS_HDR * (1 + n) + q), kin[q]);     // u'+[Nr-1] for the closure lanes
         }
       }
@@ -425,7 +431,7 @@ __device__ void solve_set_tangent_stream(const TangentArgs& ta, long long set, i
       for (int i = 0; i < K; ++i) {
         double Lv[NCY];
 #pragma unroll
-        for (int q = 0; q < NCY; ++q) Lv[q] = lds(lv_at(q, i));
+        for (int q = 0; q < NCY; ++q) Lv[q] = lv_at(q, i);
         const double Si = uv[iSFK][i], Sa = uv[aSFK][i], G1 = uv[GAB1][i], pG1 = uv[pGAB1][i], G2 = uv[GRB2][i],
                      g2g1 = uv[G2G1][i], g2pg1 = uv[G2PG1][i], S2 = uv[SHP2][i], pg1s = uv[PG1S][i], g2pg1s = uv[G2PG1S][i];
         uv[iSFK][i] = fma(cv[C_DSi], Lv[iSFK], Si + sk[i]);
@@ -505,7 +511,7 @@ __device__ void solve_set_tangent_stream(const TangentArgs& ta, long long set, i
         const T b = hdr_ld(16 + q);
         uv[q][idx_b] = b.v;
 #pragma unroll
-        for (int n = 0; n < NT; ++n) sts(sp_at(n, q, idx_b), b.p[n]);
+        for (int n = 0; n < NT; ++n) sp_at(n, q, idx_b) = b.p[n];
       }
     }
     if (track_t && t.v >= t_save) {                                 // basepdesolver.jl:912
@@ -523,7 +529,7 @@ __device__ void solve_set_tangent_stream(const TangentArgs& ta, long long set, i
 #pragma unroll
         for (int i = 0; i < K; ++i) { uv[q][i] = 0.0;
 #pragma unroll
-          for (int n = 0; n < NT; ++n) sts(sp_at(n, q, i), 0.0); }
+          for (int n = 0; n < NT; ++n) sp_at(n, q, i) = 0.0; }
       x = dconst<NT>(0.0);
     }
     double m[NMB];

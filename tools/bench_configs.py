@@ -59,6 +59,8 @@ def main():
     ap.add_argument("--configs", default="1,3,4,5")
     ap.add_argument("--scale", type=float, default=1.0, help="scale the ensemble sizes (quick runs)")
     ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--tf", type=float, default=None, help="profiling runs only: a shorter final time than the configs' tf = 5")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
     import torch
     import __graft_entry__ as g
@@ -87,6 +89,10 @@ def main():
             continue
         c = cfgs[ci]
         o = c["o"]
+        if args.tf is not None:
+            o.tf = args.tf
+            o.dt_save = args.tf / o.Nts
+            c["name"] += f" [tf = {args.tf}: NOT the config, a profiling run]"
         D = np.ascontiguousarray(c["D"], dtype=np.float64)
         k = np.ascontiguousarray(c["k"], dtype=np.float64)
         Co = np.ascontiguousarray(c["Co"], dtype=np.float64)
@@ -134,6 +140,9 @@ def main():
                             "iter_cap_sets": int((status & abi.ST_ITER_CAP != 0).sum())}
         del dout
         torch.cuda.empty_cache()
+        if args.no_e2e:
+            print(json.dumps(line), flush=True)
+            continue
         # ---- end to end through the host entry point, sharded by the library over --devices GPUs
         bufs = []
 
