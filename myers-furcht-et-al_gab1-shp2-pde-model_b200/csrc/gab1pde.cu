@@ -384,6 +384,14 @@ struct QReq {
   int64_t* n_valid;     // host
 };
 
+// bytes of device memory one shard may plan for: 85 % of the device, or GAB1_MAX_DEVICE_BYTES
+static size_t device_budget_bytes(int device) {
+  if (const char* e = getenv("GAB1_MAX_DEVICE_BYTES")) { const long long v = atoll(e); if (v > 0) return (size_t)v; }
+  size_t free_b = 0, total_b = 0;
+  if (cudaSetDevice(device) != cudaSuccess || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  return total_b / 100 * 85;
+}
+
 // One shard of the host entry point: copy in, solve, copy out, on its device's stream.
 static int run_shard(const gab1_opts* o, int device, int64_t lo, int64_t hi, const double* Co, int64_t Co_stride,
                      const double* D, const double* k, const double* dt, const double* r, double* out, int32_t* status,
@@ -392,11 +400,30 @@ static int run_shard(const gab1_opts* o, int device, int64_t lo, int64_t hi, con
   if (S <= 0) return 0;
   if (device < 0 || device >= 64) return fail(-7, "device ordinal %d out of range", device);
   CUDA_TRY(cudaSetDevice(device));
+  const int64_t nout = gab1_out_doubles_per_set(o);
+  // A shard whose staged output would not fit the device is solved in pieces, one after the other (0.5 MB per set at
+  // Nr = 50: 3e5 full solutions fill a 180 GB B200; the order statistics need the whole ensemble resident and are
+  // capped elsewhere).  GAB1_MAX_DEVICE_BYTES overrides the budget (tests).
+  bool mapped_out = false;
+  if (!qr) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, out + lo * nout) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+      mapped_out = true;              // the kernels write a pinned, mapped buffer directly: nothing is staged
+    else
+      (void)cudaGetLastError();
+  }
+  if (!qr && !mapped_out && S > 1) {
+    size_t budget = device_budget_bytes(device);
+    if (budget && (size_t)S * ((size_t)nout * sizeof(double) + 512) > budget) {
+      const int64_t mid = lo + S / 2;
+      if (int e = run_shard(o, device, lo, mid, Co, Co_stride, D, k, dt, r, out, status, n_saved, n_steps, n_bc)) return e;
+      return run_shard(o, device, mid, hi, Co, Co_stride, D, k, dt, r, out, status, n_saved, n_steps, n_bc);
+    }
+  }
   DeviceArena& ar = g_arena[device];
   std::lock_guard<std::mutex> lk(ar.mu);
   if (!ar.stream) CUDA_TRY(cudaStreamCreateWithFlags(&ar.stream, cudaStreamNonBlocking));
   cudaStream_t st = ar.stream;
-  const int64_t nout = gab1_out_doubles_per_set(o);
   const size_t P = (size_t)o->Nr + 1;
   // A pinned (mapped) caller buffer is written by the kernel directly: snapshot stores stream over PCIe while the
   // time loop runs, so there is no device copy of the 0.5 MB/set output and no D2H phase.  Pageable buffers are staged.

@@ -362,3 +362,16 @@ def test_finest_grid_all_outputs_and_edge_cases(pkg, gfe, ofe, ensemble):
     strict = pkg.host.Frontend(abi.CudaBackend(arith=abi.ARITH_STRICT))
     with pytest.raises(abi.Gab1Error, match="strict"):
         strict.pdesolver_batch(Co[:1], D[:1], k[:1], dr=0.025, tf=1e-5, Nts=2)
+
+
+def test_output_larger_than_the_device_budget_is_solved_in_pieces(pkg, gfe, ensemble, monkeypatch):
+    """A staged output that does not fit the device (3e5 full solutions fill a B200) is solved piecewise by the host entry
+    point; GAB1_MAX_DEVICE_BYTES shrinks the budget so that 96 sets x 72 KB need 16 pieces.  Results must not change."""
+    Co = pkg.params.base_Co()
+    kw = dict(dr=0.2, tf=0.2, Nts=12, tol=1e-4, maxiters=20)
+    D, k = ensemble[:96, :7], ensemble[:96, 7:]
+    whole = gfe.pdesolver_batch(Co, D, k, **kw)
+    monkeypatch.setenv("GAB1_MAX_DEVICE_BYTES", str(6 * 72 * 1024))
+    pieces = gfe.pdesolver_batch(Co, D, k, **kw)
+    assert_bits(pieces.out, whole.out, "piecewise")
+    check_control_flow(pieces, whole)
