@@ -254,6 +254,23 @@ int gab1_solve_tangent_device(const gab1_opts* o, int32_t device, void* stream, 
                               double* out, int32_t* status, int32_t* n_saved,
                               int64_t* n_steps, int64_t* n_bc_iters, void* workspace);
 
+/*
+ * Synthetic prior ensembles: the prior half of generate_ensemble (get_param_posteriors.jl:38-86) — per set,
+ * 22 independent log-normal draws exp(mu[i] + sigma[i] * z) in the order
+ *     D(7) ; Kd_S2, kS2r, Kd_G2, kG2r, kG1f, kG1r, kEGFf, kEGFr, kdf ; kG1p, kG1dp, kSa, kSi, kp, kdp
+ * assembled into D[7] and k[17] with k_f = k_r / Kd for the SHP2 and GRB2 pairs (:75-76), k[14] = EGF, kdr = kdf * Kdd.
+ * The stream is the library's own (the reference draws from Julia's default RNG): Philox4x32-10 with counter
+ * (set index, draw pair) and key = seed, two 53-bit uniforms per call, Box-Muller — any host can restate it
+ * (oracle/sampler_oracle.py).  _device: D and k are device pointers, the kernel is enqueued on `stream`; the host
+ * variant fills host buffers.
+ */
+#define GAB1_N_PRIOR_NORMALS 22
+int gab1_sample_prior_device(int32_t device, void* stream, int64_t S, uint64_t seed, const double* mu /* 22, host */,
+                             const double* sigma /* 22, host */, double EGF, double Kdd,
+                             double* D /* S x 7 */, double* k /* S x 17 */);
+int gab1_sample_prior(int64_t S, uint64_t seed, const double* mu, const double* sigma, double EGF, double Kdd,
+                      double* D, double* k);
+
 /* gab1_solve_batch keeps one slab of device memory and one stream per GPU between calls (no cudaMalloc/cudaFree per
  * call; calls that target the same GPU take turns).  This frees them; the next call re-creates what it needs. */
 void gab1_release_device_memory(void);

@@ -244,6 +244,11 @@ def load_library():
     lib.gab1_solve_tangent_device.restype = C.c_int
     lib.gab1_default_dt_tangent.argtypes = [C.c_int64, C.c_int32, _dp, _dp, C.c_double, _dp, _dp]
     lib.gab1_default_dt_tangent.restype = C.c_int
+    lib.gab1_sample_prior.argtypes = [C.c_int64, C.c_uint64, _dp, _dp, C.c_double, C.c_double, _dp, _dp]
+    lib.gab1_sample_prior.restype = C.c_int
+    lib.gab1_sample_prior_device.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_uint64, _dp, _dp, C.c_double, C.c_double,
+                                             C.c_void_p, C.c_void_p]
+    lib.gab1_sample_prior_device.restype = C.c_int
     lib.gab1_measure_fp64_tflops.argtypes = [C.c_int32, C.c_double]
     lib.gab1_measure_fp64_tflops.restype = C.c_double
     lib.gab1_debug_recip_error.argtypes = [C.c_int32, C.c_double, C.c_double, _dp, _dp]
@@ -330,6 +335,21 @@ def _default_dt_tangent(fn, D, k, dr, seeds):
     if fn(S, n_dir, _ptr(D, _dp), _ptr(k, _dp), float(dr), _ptr(dt, _dp), _ptr(seeds, _dp)) != 0:
         raise Gab1Error("default_dt_tangent failed")
     return dt, seeds
+
+
+def sample_prior(S: int, seed: int, mu, sigma, EGF: float, Kdd: float):
+    """gab1_sample_prior: S synthetic prior sets drawn on the device -> (D (S, 7), k (S, 17))."""
+    lib = load_library()
+    mu = np.ascontiguousarray(mu, dtype=np.float64)
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+    if mu.shape != (22,) or sigma.shape != (22,):
+        raise ValueError("mu and sigma must hold 22 entries")
+    D = np.zeros((S, N_D))
+    k = np.zeros((S, N_K))
+    rc = lib.gab1_sample_prior(S, seed, _ptr(mu, _dp), _ptr(sigma, _dp), float(EGF), float(Kdd), _ptr(D, _dp), _ptr(k, _dp))
+    if rc != 0:
+        raise Gab1Error(f"gab1_sample_prior failed ({rc}): {lib.gab1_last_error().decode(errors='replace')}")
+    return D, k
 
 
 def encode_probs(probs) -> np.ndarray:

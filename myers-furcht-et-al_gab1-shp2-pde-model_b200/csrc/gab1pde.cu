@@ -638,6 +638,29 @@ int gab1_default_dt_tangent(int64_t S, int32_t n_dir, const double* D, const dou
   return 0;
 }
 
+int gab1_sample_prior_device(int32_t device, void* stream, int64_t S, uint64_t seed, const double* mu, const double* sigma,
+                             double EGF, double Kdd, double* D, double* k) {
+  return gab1::sample_prior_device(device, (cudaStream_t)stream, S, seed, mu, sigma, EGF, Kdd, D, k);
+}
+
+int gab1_sample_prior(int64_t S, uint64_t seed, const double* mu, const double* sigma, double EGF, double Kdd, double* D,
+                      double* k) {
+  if (S < 0 || !mu || !sigma || !D || !k) return fail(-2, "bad arguments to gab1_sample_prior");
+  if (S == 0) return 0;
+  int visible = 0;
+  if (cudaGetDeviceCount(&visible) != cudaSuccess || visible < 1)
+    return fail(-7, "no CUDA device is visible; this library has no CPU fallback");
+  CUDA_TRY(cudaSetDevice(0));
+  double *dD = nullptr, *dk = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&dD, (size_t)S * GAB1_N_D * sizeof(double)));
+  if (cudaMalloc((void**)&dk, (size_t)S * GAB1_N_K * sizeof(double)) != cudaSuccess) { cudaFree(dD); return fail(-8, "cudaMalloc failed"); }
+  int rc = gab1::sample_prior_device(0, nullptr, S, seed, mu, sigma, EGF, Kdd, dD, dk);
+  if (!rc && cudaMemcpy(D, dD, (size_t)S * GAB1_N_D * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(-9, "copy of D failed");
+  if (!rc && cudaMemcpy(k, dk, (size_t)S * GAB1_N_K * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(-9, "copy of k failed");
+  cudaFree(dD); cudaFree(dk);
+  return rc;
+}
+
 void gab1_release_device_memory(void) {
   for (int d = 0; d < 64; ++d) {
     DeviceArena& ar = g_arena[d];

@@ -60,6 +60,9 @@ int tangent_directions_per_item(int K, int n_dir);
 int launch_tangent_kernel(int K, int NT, const TangentArgs& ta, int device, cudaStream_t stream);
 // streamed-partials kernels (tangent_stream_kernel.cuh): primal in registers, partials in shared memory; NT in {2, 4}
 int launch_tangent_stream_kernel(int K, int NT, const TangentArgs& ta, int device, cudaStream_t stream);
+// synthetic prior ensembles on the device (sampler.cu); mu, sigma are host pointers
+int sample_prior_device(int device, cudaStream_t stream, long long S, unsigned long long seed, const double* mu,
+                        const double* sigma, double EGF, double Kdd, double* D, double* k);
 // diagnostics (kernels_single.cu)
 void launch_recip_error_kernel(double lo, double hi, int n, double* out);
 

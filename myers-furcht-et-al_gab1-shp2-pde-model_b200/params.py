@@ -113,6 +113,24 @@ def synthetic_prior_ensemble(S: int, seed: int = 123) -> np.ndarray:
     return p
 
 
+# the 22 log-normal draws of one synthetic prior set, in the order gab1_sample_prior takes them (include/gab1pde.h):
+# D(7); Kd_S2, kS2r, Kd_G2, kG2r, kG1f, kG1r, kEGFf, kEGFr, kdf; kG1p, kG1dp, kSa, kSi, kp, kdp
+PRIOR_MU_SIGMA = ([_UV[n] for n in PNAMES[:7]] +
+                  [(4.09800, 1.09860), (6.17379, 0.09531), (4.09800, 1.09860), (6.17379, 0.09531), (-7.20617, 2.88008),
+                   (-2.09794, 1.14776), (4.02250, 0.49119), (-1.96105, 0.50689), (0.18232, 0.09531)] +
+                  [_UV[n] for n in ("kG1p", "kG1dp", "kSa", "kSi", "kp", "kdp")])
+PRIOR_KDD = 0.38     # kdr = kdf * Kdd
+
+
+def synthetic_prior_ensemble_device(S: int, seed: int = 123) -> np.ndarray:
+    """The distributions of synthetic_prior_ensemble drawn ON THE DEVICE (gab1_sample_prior: Philox4x32-10 + Box-Muller,
+    the library's own reproducible stream).  Returns S x 24 like its host twin (different stream)."""
+    from . import abi
+    mu, sigma = (np.array(x) for x in zip(*PRIOR_MU_SIGMA))
+    D, k = abi.sample_prior(S, seed, mu, sigma, _EGF, PRIOR_KDD)
+    return np.concatenate([D, k], axis=1)
+
+
 def resampled_ensemble(S: int, seed: int = 123) -> np.ndarray:
     """S x 24 synthetic sets with the marginals of the shipped ensemble: column-wise log-normal refit
     of parameter_ensemble.csv ("fully data-driven alternative")."""
