@@ -375,3 +375,22 @@ def test_output_larger_than_the_device_budget_is_solved_in_pieces(pkg, gfe, ense
     pieces = gfe.pdesolver_batch(Co, D, k, **kw)
     assert_bits(pieces.out, whole.out, "piecewise")
     check_control_flow(pieces, whole)
+
+
+@pytest.mark.parametrize("family", ["", "legacy", "group16", "group32", "stream"])
+def test_runs_are_bitwise_repeatable(pkg, gfe, ensemble, family, monkeypatch):
+    """compute-sanitizer is not available on this pool; a data race between lanes or warps (exchange headers, staged rows, the
+    work queue) would show up as run-to-run differences.  2500 sets (more than two waves, every warp of a CTA busy, the dynamic
+    queue in a different order each time) solved twice per kernel family must agree bit for bit."""
+    monkeypatch.setenv("GAB1_KERNEL", family)
+    Co = pkg.params.base_Co()
+    rows = np.arange(2500)
+    for dr, tf in ((0.4, 0.05), (0.2, 0.05), (0.05, 0.002)):
+        if (family == "group16" and dr < 0.2) or (family == "legacy" and dr < 0.1) or (family == "stream" and dr > 0.2):
+            continue
+        sub = rows if dr >= 0.2 else rows[:1200]
+        kw = dict(dr=dr, tf=tf, Nts=3, tol=1e-4, maxiters=20, matrices=("aSFK", "PG1Stot"))
+        a = gfe.pdesolver_batch(Co, ensemble[sub, :7], ensemble[sub, 7:], **kw)
+        b = gfe.pdesolver_batch(Co, ensemble[sub, :7], ensemble[sub, 7:], **kw)
+        assert_bits(a.out, b.out, f"{family or 'default'} dr={dr}")
+        check_control_flow(a, b)

@@ -245,3 +245,19 @@ def test_fitting_gradient_full_length(pkg, gfe, ofe):
     lo, go, yo = ofe.fitting_loss_and_gradient(x, 26.426, 9.363, **kw)
     assert np.abs(yg / yo - 1).max() < RTOL
     assert np.abs(gg - go).max() <= 1e-8 * np.abs(go).max()      # (mu - yhat) cancels: the loss gradient amplifies yhat's error
+
+
+@pytest.mark.parametrize("family", ["reg", "stream"])
+def test_tangent_runs_are_bitwise_repeatable(pkg, gfe, ensemble, family, monkeypatch):
+    """Race surrogate (no compute-sanitizer on this pool): 1500 sets x 4 directions twice, bit for bit."""
+    monkeypatch.setenv("GAB1_TANGENT", family)
+    Co = pkg.params.base_Co()
+    D, k = ensemble[:1500, :7], ensemble[:1500, 7:]
+    seeds = unit_seeds(1500, [7 + j for j in FIT_K])
+    for dr, tf in ((0.4, 0.05), (0.2, 0.03), (0.1, 0.01)):
+        kw = dict(dr=dr, tf=tf, Nts=3, tol=1e-4, maxiters=20, out_mode=pkg.abi.OUT_FINAL4)
+        a = gfe.pdesolver_tangent_batch(Co, D, k, seeds, **kw)
+        b = gfe.pdesolver_tangent_batch(Co, D, k, seeds, **kw)
+        same = (a.out.view(np.uint64) == b.out.view(np.uint64)) | (np.isnan(a.out) & np.isnan(b.out))
+        assert same.all(), f"{family} dr={dr}: {np.count_nonzero(~same)} values differ between two runs"
+        np.testing.assert_array_equal(a.n_bc_iters, b.n_bc_iters)
