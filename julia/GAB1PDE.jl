@@ -228,6 +228,19 @@ function pdesolver_fitting(p::AbstractVector{Dual{Tg,Float64,N}}; Diff_inds=1:7,
     (aSFK=mat(:aSFK), PG1S=mat(:PG1S), G2PG1S=mat(:G2PG1S), EG2PG1S=vec(:EG2PG1S)), r, vec(:t_out), dt
 end
 
+"""Synthetic prior ensemble drawn on the device (gab1_sample_prior; the prior half of generate_ensemble,
+get_param_posteriors.jl:53-76, from the library's own Philox stream): 22 log-normal (mu, sigma) in the order of include/gab1pde.h.
+Returns (Dmat S×7, kmat S×17), ready for `sapdesolver_batch` / `fbatch_*`."""
+function sample_prior(S::Integer, seed::Integer, mu::Vector{Float64}, sigma::Vector{Float64}; EGF=1.67e-3, Kdd=0.38)
+    length(mu) == 22 && length(sigma) == 22 || throw(ArgumentError("mu and sigma must hold 22 entries"))
+    Dt = zeros(Float64, 7, S); kt = zeros(Float64, 17, S)
+    rc = ccall((:gab1_sample_prior, LIB), Cint,
+               (Int64, UInt64, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ptr{Float64}, Ptr{Float64}),
+               S, seed, mu, sigma, EGF, Kdd, Dt, kt)
+    rc == 0 || error("gab1_sample_prior: " * unsafe_string(ccall((:gab1_last_error, LIB), Cstring, ())))
+    permutedims(Dt), permutedims(kt)
+end
+
 "pulsechase_solver (pulsechase_solver.jl:29-318)"
 function pulsechase_solver(Co::AbstractVector, D::AbstractVector, k::AbstractVector; R=10.0, dr=0.1, t_prechase=5.0,
                            t_chase=2.0, tf=t_prechase + t_chase, Nts=100, dt=default_dt(D, k, dr), dt_save=tf / Nts,
