@@ -13,7 +13,7 @@ int launch(const KernelArgs& args, int device, cudaStream_t stream) {
   static int blocks_per_sm[64] = {0};
   static int sms[64] = {0};
   constexpr int TPB = 32 * kWarpsPerCta;
-  const size_t smem = (size_t)kWarpsPerCta * (WS_HDR + 2 * (size_t)args.P_pad) * sizeof(double);
+  const size_t smem = (size_t)kWarpsPerCta * (WS_HDR + 2 * (size_t)args.P_pad + WS_EX) * sizeof(double);
   auto kern = solve_kernel<K, MODE>;
   {
     std::lock_guard<std::mutex> lk(mu);

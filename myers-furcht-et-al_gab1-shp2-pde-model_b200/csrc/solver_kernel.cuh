@@ -33,6 +33,11 @@ enum { mE, mES, mESmES, E, EG2, EG2G1, EG2PG1, EG2PG1S, NMB };                  
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int WS_HDR = 32;          // per-warp smem header: [0,16) interior-neighbour stage, [16,32) boundary stage
 constexpr int ML = 10;              // first membrane lane
+// Halo exchange area of the fast one-set-per-warp kernel with K >= 4 nodes per lane: the interior halo crosses lanes
+// through shared memory (20 STS.64 + 20 LDS.64 per step) instead of 40 32-bit shuffles plus the register moves that
+// re-pair their halves.  Measured on B200: K = 4 (dr = 0.1) 378.9 vs 388.9 ms; K = 2 (dr = 0.2) 126.8 vs 117.2 ms — with
+// two nodes per lane there is too little independent work to cover store -> warp barrier -> load, so K <= 2 keeps shuffles.
+constexpr int WS_EX = 2 * 10 * 32;  // doubles per warp: [species][lane] of the last node, then of the first node
 
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -672,10 +677,26 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
       // ---- interior: D*lap + kinetics, explicit Euler, updated in place (basepdesolver.jl:150-180) ----
       {
         double hl[NCY], hr[NCY];
+        if constexpr (K >= 4) {
+          const unsigned ex = ws_s + 8u * (unsigned)(WS_HDR + 2 * a.P_pad);
 #pragma unroll
-        for (int q = 0; q < NCY; ++q) {
-          hl[q] = shfl_up1(u[q][K - 1]);
-          hr[q] = shfl_down1(u[q][0]);
+          for (int q = 0; q < NCY; ++q) {
+            sts(ex + 8u * (unsigned)(q * 32 + lane), u[q][K - 1]);
+            sts(ex + 8u * (unsigned)((NCY + q) * 32 + lane), u[q][0]);
+          }
+          __syncwarp();
+          const int ll = lane > 0 ? lane - 1 : 0, lr = lane < 31 ? lane + 1 : 31;
+#pragma unroll
+          for (int q = 0; q < NCY; ++q) {
+            hl[q] = lds(ex + 8u * (unsigned)(q * 32 + ll));
+            hr[q] = lds(ex + 8u * (unsigned)((NCY + q) * 32 + lr));
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < NCY; ++q) {
+            hl[q] = shfl_up1(u[q][K - 1]);
+            hr[q] = shfl_down1(u[q][0]);
+          }
         }
         double L[2][NCY];     // Laplacians of the node being updated and of the next one (which still needs old values)
 #pragma unroll
@@ -893,7 +914,7 @@ solve_kernel(const KernelArgs a) {
   if (a.guard && *a.guard != a.guard_expect) return;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* ws = smem + (size_t)warp * (WS_HDR + 2 * a.P_pad);
+  double* ws = smem + (size_t)warp * (WS_HDR + 2 * a.P_pad + WS_EX);
   const int Nr = a.o.Nr;
   ws[lane] = 0.0;
   __syncwarp();
