@@ -96,8 +96,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_sample(pkg, nsets_per_thread=12):
-    """Times the oracle (C restatement of the reference CPU path) on a bounded sample of the same workload."""
+def cpu_sample(pkg, nsets_per_thread=32):
+    """Times the oracle (C restatement of the reference CPU path) on a bounded sample of the same workload: 32 sets per host
+    thread (about 20 CPU-seconds on 16 threads; enough sets per thread for the dynamic schedule to balance)."""
     from oracle import oracle
     o, Co, D, k, dt, r = workload(pkg)
     threads = oracle.max_threads()
