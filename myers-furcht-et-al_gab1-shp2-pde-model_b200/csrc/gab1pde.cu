@@ -183,6 +183,24 @@ int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long 
   //      Nr = 200, 1184 sets: 1667 ms against 2808 ms for the register-resident K = 8 kernel (which spills its state);
   //      Nr = 100: 416 vs 392 ms, Nr = 50: 191 vs 117 ms — the register kernels keep the small grids.
   //      GAB1_KERNEL=stream forces this family for Nr > 32 (A/B measurements, parity tests).
+  // ---- small batches: one CTA per set (team_kernel.cuh).  GAB1_TEAM_MAX_SETS overrides the measured threshold.
+  if (mode != gab1::MODE_STRICT && o->Nr > 32 && o->Nr <= 256) {
+    const char* e = getenv("GAB1_KERNEL");
+    const bool named = e && e[0];
+    // Measured crossover on B200 (tools/bench_small.py): teams of 2 warps (Nr <= 64) lose to one warp per
+    // set even for a single solve (22 vs 15 ms); teams of 4 win 1.47x up to 148 sets and 1.17x at 296, lose at 592; teams of 7
+    // win 2.75x for one set, 1.65x at 296, lose at 592.  Rule: all teams resident at <= 8 warps per SM (16 for 6+ warps).
+    long long max_sets = 0;
+    if (o->Nr > 64) {
+      const int W = (o->Nr + 31) / 32;
+      int nsm = 148;
+      (void)cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+      max_sets = (long long)nsm * (W >= 6 ? 16 : 8) / W;
+    }
+    if (const char* m = getenv("GAB1_TEAM_MAX_SETS")) max_sets = atoll(m);
+    if ((named && strcmp(e, "team") == 0) || (!named && S <= max_sets))
+      return gab1::launch_team_kernel(mode, a, device, stream);
+  }
   if (mode != gab1::MODE_STRICT) {
     const char* e = getenv("GAB1_KERNEL");
     const bool forced = e && strcmp(e, "stream") == 0 && o->Nr > 32;

@@ -44,6 +44,8 @@ int launch_group16_kernel(int K, int variant, int mode, bool mirror, const Kerne
 int launch_group32_kernel(int K, int variant, int mode, bool mirror, const KernelArgs& args, int device, cudaStream_t stream);
 // shared-memory-resident solver for large grids (stream_kernel.cuh): K in {2, 4, 8, 16} nodes per lane, fast modes only
 int launch_stream_kernel(int K, int mode, const KernelArgs& args, int device, cudaStream_t stream);
+// latency kernel (team_kernel.cuh): one CTA of ceil(Nr/32) warps per set, 32 < Nr <= 256, fast modes only
+int launch_team_kernel(int mode, const KernelArgs& args, int device, cudaStream_t stream);
 // order statistics across the sets of a FULL result (ensemble_stats.cu); all pointers but `p` are device pointers
 size_t quantiles_workspace_bytes(long long S);
 int ensemble_quantiles_device(const gab1_opts* o, int device, cudaStream_t stream, long long S, const double* out,

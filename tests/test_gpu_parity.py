@@ -294,6 +294,8 @@ FAMILIES = {
     "group32t": [0.2],
     # state in shared memory (stream_kernel.cuh): K = 4, 8, 16 nodes per lane; dr = 0.025 (Nr = 400) exists only here
     "stream": [0.2, 0.1, 0.05, 0.025],
+    # latency path: one CTA of 2 / 4 / 7 warps per set (team_kernel.cuh)
+    "team": [0.25, 0.2, 0.1, 0.05],
 }
 
 
@@ -377,7 +379,7 @@ def test_output_larger_than_the_device_budget_is_solved_in_pieces(pkg, gfe, ense
     check_control_flow(pieces, whole)
 
 
-@pytest.mark.parametrize("family", ["", "legacy", "group16", "group32", "stream"])
+@pytest.mark.parametrize("family", ["", "legacy", "group16", "group32", "stream", "team"])
 def test_runs_are_bitwise_repeatable(pkg, gfe, ensemble, family, monkeypatch):
     """compute-sanitizer is not available on this pool; a data race between lanes or warps (exchange headers, staged rows, the
     work queue) would show up as run-to-run differences.  2500 sets (more than two waves, every warp of a CTA busy, the dynamic
@@ -386,7 +388,7 @@ def test_runs_are_bitwise_repeatable(pkg, gfe, ensemble, family, monkeypatch):
     Co = pkg.params.base_Co()
     rows = np.arange(2500)
     for dr, tf in ((0.4, 0.05), (0.2, 0.05), (0.05, 0.002)):
-        if (family == "group16" and dr < 0.2) or (family == "legacy" and dr < 0.1) or (family == "stream" and dr > 0.2):
+        if (family == "group16" and dr < 0.2) or (family == "legacy" and dr < 0.1) or (family in ("stream", "team") and dr > 0.2):
             continue
         sub = rows if dr >= 0.2 else rows[:1200]
         kw = dict(dr=dr, tf=tf, Nts=3, tol=1e-4, maxiters=20, matrices=("aSFK", "PG1Stot"))
