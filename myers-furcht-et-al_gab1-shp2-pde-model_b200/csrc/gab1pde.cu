@@ -197,7 +197,7 @@ int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long 
       (void)cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
       max_sets = (long long)nsm * (W >= 6 ? 16 : 8) / W;
     }
-    if (const char* m = getenv("GAB1_TEAM_MAX_SETS")) max_sets = atoll(m);
+    if (const char* m = getenv("GAB1_TEAM_MAX_SETS")) { if (m[0]) max_sets = atoll(m); }
     if ((named && strcmp(e, "team") == 0) || (!named && S <= max_sets))
       return gab1::launch_team_kernel(mode, a, device, stream);
   }

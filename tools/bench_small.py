@@ -15,6 +15,7 @@ for dr, tf in ((0.2, 5.0), (0.1, 5.0), (0.05, 1.0)):
         out = {}
         for fam in ("", "team"):
             os.environ["GAB1_KERNEL"] = fam
+            os.environ["GAB1_TEAM_MAX_SETS"] = "0" if fam == "" else ""      # "": the throughput kernels, never the team kernel
             kw = dict(dr=dr, tf=tf, out_mode=pkg.abi.OUT_FINAL4)
             fe.sapdesolver_batch(Co, ens[:2, :7], ens[:2, 7:], dr=dr, tf=0.01, out_mode=pkg.abi.OUT_FINAL4)
             t0 = time.perf_counter()
