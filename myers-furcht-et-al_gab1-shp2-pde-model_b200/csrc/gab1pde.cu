@@ -269,8 +269,17 @@ int solve_tangent_device(const gab1_opts* o, int device, cudaStream_t stream, lo
   //   64 < Nr <= 128  streamed kernel, 4 directions per item   (16.2x; register kernel with 1: 26.8x)
   //   one direction   register kernel
   // GAB1_TANGENT = reg | stream and GAB1_TANGENT_NT = 1 | 2 | 4 override for A/B measurements.
+  //   small batches   register kernel, ONE direction per item: while every (set, direction) pair gets a warp of its own
+  //                   with at most one warp per scheduler, latency is what counts — one loss-and-gradient evaluation with
+  //                   4 partials: dr = 0.2 59 ms (2 per item: 88 ms), dr = 0.1 581 ms (streamed, 4 per item: 1202 ms);
+  //                   a 101-point multistart population: 168 vs 223 ms and 651 vs 1304 ms (tools/tangent_latency.sh)
   bool streamed = n_dir >= 2 && K != 2;
   int NT = n_dir == 1 ? 1 : (K == 4 && n_dir >= 3 ? 4 : 2);
+  {
+    int nsm = 148;
+    (void)cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+    if (S * (long long)n_dir <= 4LL * nsm) { streamed = false; NT = 1; }
+  }
   if (const char* e = getenv("GAB1_TANGENT")) {
     if (strcmp(e, "reg") == 0) { streamed = false; NT = gab1::tangent_directions_per_item(K, n_dir); }
     if (strcmp(e, "stream") == 0) { streamed = true; NT = n_dir >= 3 ? 4 : 2; }
