@@ -288,6 +288,16 @@ int solve_tangent_device(const gab1_opts* o, int device, cudaStream_t stream, lo
     const int v = atoi(e);
     if (streamed ? (v == 2 || v == 4) : ((v == 1) || (v == 2 && K <= 2) || (v == 4 && K == 1))) NT = v;
   }
+  // one CTA per (set, direction) while every one of them is resident (team_tangent_kernel.cuh; measured in DESIGN.md section 8)
+  bool team = false;
+  if (o->Nr > 64 && o->Nr <= 256) {
+    int nsm = 148;
+    (void)cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+    // dr = 0.1, one / 37 / 101 evaluations with 4 partials: 127 / 138 / 309 ms against 577 / 628 / 654 ms for one warp per
+    // (set, direction); two CTAs are resident per SM, so 8 * SMs items are four rounds of ~130 ms
+    team = S * (long long)n_dir <= 8LL * nsm;
+    if (const char* e = getenv("GAB1_TANGENT")) { if (strcmp(e, "team") == 0) team = true; else if (e[0]) team = false; }
+  }
   ta.groups = (n_dir + NT - 1) / NT;
   CUDA_TRY(cudaMemsetAsync(w.counter, 0, sizeof(unsigned), stream));
   const int tb = 256;
@@ -298,6 +308,7 @@ int solve_tangent_device(const gab1_opts* o, int device, cudaStream_t stream, lo
   size_t bytes = w.cub_bytes;
   CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp, bytes, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)S,
                                                      0, 32, stream));
+  if (team) return gab1::launch_team_tangent_kernel(ta, device, stream);
   return streamed ? gab1::launch_tangent_stream_kernel(K, NT, ta, device, stream)
                   : gab1::launch_tangent_kernel(K, NT, ta, device, stream);
 }

@@ -3,6 +3,7 @@
 
 #include "launch.h"
 #include "team_kernel.cuh"
+#include "team_tangent_kernel.cuh"
 
 namespace gab1 {
 namespace {
@@ -35,6 +36,34 @@ int launch(const KernelArgs& args, int device, cudaStream_t stream) {
   return 0;
 }
 }  // namespace
+
+int launch_team_tangent_kernel(const TangentArgs& ta, int device, cudaStream_t stream) {
+  const int W = (ta.a.o.Nr + 31) / 32;
+  const int T = 32 * W;
+  if (T > 256) return fail(-6, "team tangent kernel: Nr = %d needs more than 8 warps", ta.a.o.Nr);
+  const size_t smem = ((size_t)4 * NCY * T + WS_HDR + (size_t)ta.a.P_pad) * sizeof(double);
+  static std::mutex mu;
+  static bool attr_set[64] = {false};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 64 && !attr_set[device]) {
+      CUDA_TRY(cudaFuncSetAttribute(team_tangent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set[device] = true;
+    }
+  }
+  int nb = 0, nsm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, team_tangent_kernel, T, smem));
+  CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+  if (nb < 1) return fail(-5, "team tangent kernel does not fit on an SM (T=%d, smem=%zu)", T, smem);
+  long long grid = (long long)nsm * nb;
+  const long long items = ta.a.S * (long long)ta.n_dir;
+  if (grid > items) grid = items;
+  if (grid < 1) grid = 1;
+  team_tangent_kernel<<<(unsigned)grid, T, smem, stream>>>(ta);
+  count_launch();
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
 
 int launch_team_kernel(int mode, const KernelArgs& a, int device, cudaStream_t stream) {
   return mode == MODE_FAST_WHILE ? launch<MODE_FAST_WHILE>(a, device, stream) : launch<MODE_FAST_FOR>(a, device, stream);

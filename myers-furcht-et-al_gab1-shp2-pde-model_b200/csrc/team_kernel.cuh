@@ -91,6 +91,7 @@ team_kernel(const KernelArgs a) {
       u_at(0, GRB2, tid) = on ? CoG2 : 0.0;
       u_at(0, SHP2, tid) = on ? CoS2 : 0.0;
     }
+    __syncthreads();                                     // the initial state is visible to the neighbours
     int cur = 0;                                         // buffer holding the current time level
     // value of node n (0..Nr) of species q in buffer b; node 0 mirrors node 1
     auto at_node = [&](int b, int q, int n) -> double { return u_at(b, q, (n < 1 ? 1 : n) - off); };

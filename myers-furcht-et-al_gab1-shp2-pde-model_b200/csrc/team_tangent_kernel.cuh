@@ -1,0 +1,391 @@
+// team_tangent_kernel.cuh — LATENCY path of forward mode: one CTA per (parameter set, direction), one thread per node.
+//
+// LBFGS and NUTS ask for one loss-and-gradient evaluation at a time (param_fitting+inference_finitediff.jl:238-270,
+// 308-370), and the final optimisation stage runs at dr = 0.1: with one warp per (set, direction) that is 140 116
+// steps of a lone warp that carries four nodes per lane and spills (572 ms per gradient).  Here the team layout of
+// team_kernel.cuh carries a dual number per node: value and ONE partial of all ten species as a ping-pong pair in
+// shared memory, thread t = node t, the last warp runs the lane-parallel fixed point on duals (tangent_kernel.cuh),
+// one __syncthreads() per step.  The four directions of a gradient are four CTAs.
+// Same restrictions as gab1_solve_tangent; arithmetic forms as tangent_kernel.cuh.
+#pragma once
+#include "tangent_kernel.cuh"
+
+namespace gab1 {
+
+__global__ void __launch_bounds__(256)
+team_tangent_kernel(const TangentArgs ta) {
+  typedef Dn<1> D1;
+  const KernelArgs& a = ta.a;
+  extern __shared__ double smem[];
+  __shared__ unsigned s_item;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x, W = T >> 5;
+  const bool mwarp = warp == W - 1;
+  const int Nr = a.o.Nr, P = Nr + 1, Nts = a.o.Nts, Cn = Nts + 1;
+  const int off = Nr - (T - 1);
+  const int node = tid + off;
+  double* U = smem;                                    // [2 buffers][2 components][NCY][T]
+  double* hdr = smem + 4 * NCY * T;                    // [0,16): membrane values, [16,32): their partials
+  double* row = hdr + WS_HDR;                          // P_pad doubles
+  auto u_at = [&](int buf, int c, int q, int slot) -> double& { return U[((buf * 2 + c) * NCY + q) * T + slot]; };
+
+  const bool interior = node >= 1 && node <= Nr - 1;
+  double cpc = 0.0, cmc = 0.0, c0c = 0.0;
+  {
+    const double dr = a.o.dr, inv_dr2 = 1.0 / (dr * dr);
+    const double r = (node >= 1 && node <= Nr) ? a.r[node] : 1.0;
+    const double aj = (a.o.geometry == GAB1_GEOM_SPHERICAL) ? 1.0 / (r * dr) : 0.0;
+    double cp = inv_dr2 + aj, cm = inv_dr2 - aj, c0 = -2.0 * inv_dr2;
+    if (node == 1) { c0 += cm; cm = 0.0; }
+    if (interior) { cpc = cp; cmc = cm; c0c = c0; }
+  }
+  const int sl = tid > 0 ? tid - 1 : 0, sr = tid < T - 1 ? tid + 1 : T - 1;
+  const long long items = a.S * (long long)ta.n_dir;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(a.counter, 1u);
+    __syncthreads();
+    const unsigned item = s_item;
+    if ((long long)item >= items) break;
+    const long long si = item / ta.n_dir;
+    const int dir = (int)(item - si * ta.n_dir);
+    const long long set = a.order ? (long long)a.order[si] : si;
+    const bool lead = dir == 0;                          // owns the value block and the diagnostics
+
+    const long long nout = a.out_stride;
+    double* oset = a.out + set * nout * (1 + ta.n_dir);
+    double* ob[2] = {lead ? oset : nullptr, oset + (long long)(1 + dir) * nout};
+    unsigned status = 0;
+    const double* Cov = a.Co + set * a.Co_stride;
+    const double* Dv = a.D + set * GAB1_N_D;
+    const double* kv = a.k + set * GAB1_N_K;
+    const double* sd = ta.seeds + (set * ta.n_dir + dir) * GAB1_N_SEED;
+    auto Dd = [&](int i) { D1 r; r.v = Dv[i]; r.p[0] = sd[i]; return r; };
+    auto kd = [&](int i) { D1 r; r.v = kv[i]; r.p[0] = sd[GAB1_N_D + i]; return r; };
+    auto Cod = [&](int i) { D1 r; r.v = Cov[i]; r.p[0] = sd[GAB1_N_D + GAB1_N_K + i]; return r; };
+    D1 dt; dt.v = a.dt[set]; dt.p[0] = sd[GAB1_N_SEED - 1];
+    const D1 CoSFK = Cod(0), CoG2 = Cod(1), CoG1 = Cod(2), CoS2 = Cod(3), CoEGFR = Cod(4);
+    D1 D_Si = Dd(0), D_Sa = Dd(0);
+    if (a.o.sfk_mode == GAB1_SFK_MEMBRANE) D_Sa = dconst<1>(1e-32);
+    if (a.o.sfk_mode == GAB1_SFK_BOTH_FROZEN) { D_Si = dconst<1>(1e-32); D_Sa = dconst<1>(1e-32); }
+    const bool track_t = (a.o.out_mode == GAB1_OUT_FULL || a.o.out_mode == GAB1_OUT_PCT_BOUND);
+
+    const double nt_f = ceil(__ddiv_rn(a.o.tf, dt.v));
+    if (!(nt_f >= 0.0 && nt_f < 9.0e18)) {
+      for (int c = 0; c < 2; ++c)
+        if (ob[c]) for (long long i = tid; i < nout; i += T) ob[c][i] = 0.0;
+      if (lead && tid == 0) {
+        if (a.status) a.status[set] = GAB1_ST_THROW;
+        if (a.n_saved) a.n_saved[set] = 0;
+        if (a.n_steps) a.n_steps[set] = 0;
+        if (a.n_bc) a.n_bc[set] = 0;
+      }
+      continue;
+    }
+    const long long Nt = (long long)nt_f;
+
+    {
+      const bool on = node >= 1 && node <= Nr;
+#pragma unroll
+      for (int q = 0; q < NCY; ++q) { u_at(0, 0, q, tid) = 0.0; u_at(0, 1, q, tid) = 0.0; u_at(1, 0, q, tid) = 0.0; u_at(1, 1, q, tid) = 0.0; }
+      u_at(0, 0, iSFK, tid) = on ? CoSFK.v : 0.0; u_at(0, 1, iSFK, tid) = on ? CoSFK.p[0] : 0.0;
+      u_at(0, 0, GAB1, tid) = on ? CoG1.v : 0.0;  u_at(0, 1, GAB1, tid) = on ? CoG1.p[0] : 0.0;
+      u_at(0, 0, GRB2, tid) = on ? CoG2.v : 0.0;  u_at(0, 1, GRB2, tid) = on ? CoG2.p[0] : 0.0;
+      u_at(0, 0, SHP2, tid) = on ? CoS2.v : 0.0;  u_at(0, 1, SHP2, tid) = on ? CoS2.p[0] : 0.0;
+      if (tid < WS_HDR) hdr[tid] = 0.0;
+    }
+    __syncthreads();                                     // the initial state is visible to the neighbours
+    int cur = 0;
+    auto at_node = [&](int b, int c, int q, int n) -> double { return u_at(b, c, q, (n < 1 ? 1 : n) - off); };
+    auto stot_at = [&](int b, int c, int n) { return __dadd_rn(at_node(b, c, PG1S, n), at_node(b, c, G2PG1S, n)); };
+    auto ptot_at = [&](int b, int c, int n) {
+      const double g2pg1 = at_node(b, c, G2PG1, n), pg1 = at_node(b, c, pGAB1, n), pg1s = at_node(b, c, PG1S, n), g2pg1s = at_node(b, c, G2PG1S, n);
+      if (a.o.pg1tot_form == GAB1_PG1TOT_VIA_STOT) return __dadd_rn(__dadd_rn(g2pg1, pg1), __dadd_rn(pg1s, g2pg1s));
+      return __dadd_rn(__dadd_rn(__dadd_rn(g2pg1, pg1), pg1s), g2pg1s);
+    };
+
+    if (a.o.out_mode == GAB1_OUT_FULL) {
+      for (int c = 0; c < 2; ++c) {
+        if (!ob[c]) continue;
+        auto comp = [&](const D1& x) { return c == 0 ? x.v : x.p[0]; };
+        long long o2 = 0;
+        for (int mi = 0; mi < 12; ++mi) {
+          if (!((a.o.matrix_mask >> mi) & 1u)) continue;
+          const double v0 = mi == GAB1_M_iSFK ? comp(CoSFK) : mi == GAB1_M_GRB2 ? comp(CoG2) : mi == GAB1_M_SHP2 ? comp(CoS2)
+                            : mi == GAB1_M_GAB1 ? comp(CoG1) : 0.0;
+          for (int n = tid; n < P; n += T) ob[c][o2 + n] = v0;
+          o2 += (long long)P * Cn;
+        }
+        if (tid < GAB1_N_VECTORS) ob[c][o2 + (long long)tid * Cn] = tid == GAB1_V_mE ? comp(CoEGFR) : 0.0;
+      }
+    }
+
+    D1 t = dconst<1>(0.0);
+    double t_save = a.o.dt_save;
+    int nts = 1;
+    long long bc_total = 0;
+    D1 pct_ave = dconst<1>(0.0), pct_memb = dconst<1>(0.0);
+
+    const D1 kS2f_t = kd(0) * dt, kS2r_t = kd(1) * dt, kG1f_t = kd(2) * dt, kG1r_t = kd(3) * dt, kG1p_t = kd(6) * dt,
+             kG1dp_t = kd(7) * dt, kSi_t = kd(9) * dt;
+    const D1 Dt_Si = D_Si * dt, Dt_Sa = D_Sa * dt, Dt_G1 = Dd(4) * dt, Dt_G2 = Dd(1) * dt, Dt_G2G1 = Dd(2) * dt,
+             Dt_S2 = Dd(6) * dt, Dt_G1S2 = Dd(5) * dt, Dt_G2G1S2 = Dd(3) * dt;
+
+    // ---- membrane block: lane roles of the last warp (tangent_kernel.cuh) ----
+    constexpr int LZ = 31, LE = ML + NMB;
+    D1 kf = dconst<1>(0.0), kr = dconst<1>(0.0), Dq = dconst<1>(1.0);
+    int src_num = LZ, src_den = LZ;
+    switch (lane) {
+      case iSFK:   kf = kd(8); Dq = D_Si; src_den = LE; break;
+      case aSFK:   kf = kd(8); Dq = D_Si; src_num = LE; src_den = LE; break;
+      case GAB1:   kf = kd(2); kr = kd(3); Dq = Dd(4); src_num = ML + EG2G1;   src_den = ML + EG2;    break;
+      case pGAB1:  kf = kd(2); kr = kd(3); Dq = Dd(4); src_num = ML + EG2PG1;  src_den = ML + EG2;    break;
+      case GRB2:   kf = kd(4); kr = kd(5); Dq = Dd(1); src_num = ML + EG2;     src_den = ML + E;      break;
+      case G2G1:   kf = kd(4); kr = kd(5); Dq = Dd(2); src_num = ML + EG2G1;   src_den = ML + E;      break;
+      case G2PG1:  kf = kd(4); kr = kd(5); Dq = Dd(2); src_num = ML + EG2PG1;  src_den = ML + E;      break;
+      case SHP2:   kf = kd(0); kr = kd(1); Dq = Dd(6); src_num = ML + EG2PG1S; src_den = ML + EG2PG1; break;
+      case PG1S:   kf = kd(2); kr = kd(3); Dq = Dd(5); src_num = ML + EG2PG1S; src_den = ML + EG2;    break;
+      case G2PG1S: kf = kd(4); kr = kd(5); Dq = Dd(3); src_num = ML + EG2PG1S; src_den = ML + E;      break;
+      default: break;
+    }
+    const D1 drD = drdiv<1>(a.o.dr, Dq);
+    const D1 cf = kf * drD;
+    const D1 cr_fixed = kr * drD;
+    const D1 ca = kd(8) * drdiv<1>(a.o.dr, D_Sa);
+    const bool is_flux = lane >= GAB1 && lane <= G2PG1S;
+    const D1 kf_t = is_flux ? kf * dt : dconst<1>(0.0), kr_t = is_flux ? kr * dt : dconst<1>(0.0);
+    int fs0 = LZ, fs1 = LZ, fs2 = LZ, fs3 = LZ;
+    double sg0 = 0.0, sg1 = 0.0, sg2 = 0.0, sg3 = 0.0;
+    switch (lane - ML) {
+      case E:       fs0 = GRB2;   fs1 = G2G1;  fs2 = G2PG1; fs3 = G2PG1S; sg0 = -1.0; sg1 = -1.0; sg2 = -1.0; sg3 = -1.0; break;
+      case EG2:     fs0 = GRB2;   fs1 = GAB1;  fs2 = pGAB1; fs3 = PG1S;   sg0 = 1.0;  sg1 = -1.0; sg2 = -1.0; sg3 = -1.0; break;
+      case EG2G1:   fs0 = G2G1;   fs1 = GAB1;  sg0 = 1.0; sg1 = 1.0; break;
+      case EG2PG1:  fs0 = G2PG1;  fs1 = pGAB1; fs2 = SHP2; sg0 = 1.0; sg1 = 1.0; sg2 = -1.0; break;
+      case EG2PG1S: fs0 = G2PG1S; fs1 = PG1S;  fs2 = SHP2; sg0 = 1.0; sg1 = 1.0; sg2 = 1.0; break;
+      default: break;
+    }
+    D1 alpha = dconst<1>(0.0), alpha2 = dconst<1>(0.0), beta = dconst<1>(0.0);
+    double s_own = 0.0, s_src = 0.0;
+    int f_src = LZ;
+    switch (lane - ML) {
+      case mE:     alpha = kd(12) * kd(14); beta = kd(13); s_own = -1.0; break;
+      case mES:    alpha2 = kd(15);         beta = kd(16); s_own = -2.0; s_src = 1.0; f_src = ML + mE; break;
+      case mESmES: alpha = kd(10);          beta = kd(11); s_own = -1.0; s_src = 1.0; f_src = ML + mES; break;
+      case E:      s_src = 1.0; f_src = ML + mESmES; break;
+      case NMB:    s_src = 2.0; f_src = ML + mESmES; break;
+      default: break;
+    }
+    const double tol = a.o.tol;
+    const bool untracked = lane >= LE;
+    const int maxiters = a.o.maxiters;
+    D1 x = (lane == ML + mE) ? CoEGFR : dconst<1>(0.0);
+
+    auto publish_m = [&]() { if (mwarp && lane >= ML && lane < LE) { hdr[lane - ML] = x.v; hdr[16 + lane - ML] = x.p[0]; } };
+    // one snapshot column, both components; hdr holds the membrane values (after publish_m + __syncthreads)
+    auto write_column = [&](int col, int b) {
+      constexpr int kSpecies[10] = {iSFK, aSFK, GRB2, GAB1, SHP2, G2G1, G2PG1, G2PG1S, pGAB1, PG1S};
+      for (int c = 0; c < 2; ++c) {
+        if (!ob[c]) continue;
+        long long o2 = 0;
+        for (int mi = 0; mi < 12; ++mi) {
+          if (!((a.o.matrix_mask >> mi) & 1u)) continue;
+          for (int n = tid; n < P; n += T)
+            ob[c][o2 + (long long)col * P + n] = mi < 10 ? at_node(b, c, kSpecies[mi], n) : (mi == GAB1_M_PG1tot ? ptot_at(b, c, n) : stot_at(b, c, n));
+          o2 += (long long)P * Cn;
+        }
+        if (tid == 0) {
+          const double* m = hdr + 16 * c;
+          double* v = ob[c] + o2;
+          const double Etot = 2.0 * (m[E] + m[EG2] + m[EG2G1] + m[EG2PG1] + m[EG2PG1S]);
+          if (c == 0) {
+            v[GAB1_V_pE * (long long)Cn + col] = __ddiv_rn(__dmul_rn(__dmul_rn(2.0, __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(m[E], m[EG2]), m[EG2G1]), m[EG2PG1]), m[EG2PG1S])), 100.0), CoEGFR.v);
+            v[GAB1_V_EGFR_SHP2 * (long long)Cn + col] = __ddiv_rn(__dmul_rn(m[EG2PG1S], 100.0), CoEGFR.v);
+            v[GAB1_V_t_out * (long long)Cn + col] = t.v;
+          } else {                                             // quotient rule for the two outputs that divide by CoEGFR
+            const double* mv = hdr;
+            const double Etot_v = 2.0 * (mv[E] + mv[EG2] + mv[EG2G1] + mv[EG2PG1] + mv[EG2PG1S]);
+            const double w = CoEGFR.p[0] / CoEGFR.v;
+            v[GAB1_V_pE * (long long)Cn + col] = (Etot * 100.0) / CoEGFR.v - (Etot_v * 100.0 / CoEGFR.v) * w;
+            v[GAB1_V_EGFR_SHP2 * (long long)Cn + col] = (m[EG2PG1S] * 100.0) / CoEGFR.v - (mv[EG2PG1S] * 100.0 / CoEGFR.v) * w;
+            v[GAB1_V_t_out * (long long)Cn + col] = t.p[0];
+          }
+          v[GAB1_V_mE * (long long)Cn + col] = m[mE];
+          v[GAB1_V_mES * (long long)Cn + col] = m[mES];
+          v[GAB1_V_mESmES * (long long)Cn + col] = m[mESmES];
+          v[GAB1_V_E * (long long)Cn + col] = m[E];
+          v[GAB1_V_EG2 * (long long)Cn + col] = m[EG2];
+          v[GAB1_V_EG2G1 * (long long)Cn + col] = m[EG2G1];
+          v[GAB1_V_EG2PG1 * (long long)Cn + col] = m[EG2PG1];
+          v[GAB1_V_EG2PG1S * (long long)Cn + col] = m[EG2PG1S];
+        }
+      }
+      bool ns = false;
+      for (int n = tid; n < P; n += T) ns |= isnan(at_node(b, 0, PG1S, n));
+      if (ns) status |= GAB1_ST_NAN;
+    };
+
+    for (long long step = 1; step <= Nt; ++step) {
+      const int nxt = cur ^ 1;
+      // ---- interior on duals: thread = node, old buffer -> new buffer ----
+      {
+        auto ldq = [&](int q, int slot) { D1 r; r.v = u_at(cur, 0, q, slot); r.p[0] = u_at(cur, 1, q, slot); return r; };
+        const D1 Si = ldq(iSFK, tid), Sa = ldq(aSFK, tid), G1 = ldq(GAB1, tid), pG1 = ldq(pGAB1, tid), G2 = ldq(GRB2, tid),
+                 g2g1 = ldq(G2G1, tid), g2pg1 = ldq(G2PG1, tid), S2 = ldq(SHP2, tid), pg1s = ldq(PG1S, tid), g2pg1s = ldq(G2PG1S, tid);
+        auto lap = [&](int q, const D1& uc) {
+          const D1 up = ldq(q, sr), um = ldq(q, sl);
+          D1 r;
+          r.v = fma(cpc, up.v, fma(cmc, um.v, c0c * uc.v));
+          r.p[0] = fma(cpc, up.p[0], fma(cmc, um.p[0], c0c * uc.p[0]));
+          return r;
+        };
+        auto stq = [&](int q, const D1& val) { u_at(nxt, 0, q, tid) = val.v; u_at(nxt, 1, q, tid) = val.p[0]; };
+        const D1 gb = kG1f_t * G2, ph = kG1p_t * Sa, sb = kS2f_t * S2;
+        const D1 v1 = dfms<1>(gb, G1, kG1r_t * g2g1);
+        const D1 v3 = dfms<1>(gb, pG1, kG1r_t * g2pg1);
+        const D1 v5 = dfms<1>(gb, pg1s, kG1r_t * g2pg1s);
+        const D1 v2 = dfms<1>(ph, G1, kG1dp_t * pG1);
+        const D1 v6 = dfms<1>(ph, g2g1, kG1dp_t * g2pg1);
+        const D1 v4 = dfms<1>(sb, pG1, kS2r_t * pg1s);
+        const D1 v7 = dfms<1>(sb, g2pg1, kS2r_t * g2pg1s);
+        const D1 sk = kSi_t * Sa;
+        stq(iSFK, dfma<1>(Dt_Si, lap(iSFK, Si), Si + sk));
+        stq(aSFK, dfma<1>(Dt_Sa, lap(aSFK, Sa), Sa - sk));
+        stq(GAB1, dfma<1>(Dt_G1, lap(GAB1, G1), G1 - v1 - v2));
+        stq(pGAB1, dfma<1>(Dt_G1, lap(pGAB1, pG1), pG1 - v3 + v2 - v4));
+        stq(GRB2, dfma<1>(Dt_G2, lap(GRB2, G2), G2 - v1 - v3 - v5));
+        stq(G2G1, dfma<1>(Dt_G2G1, lap(G2G1, g2g1), g2g1 + v1 - v6));
+        stq(G2PG1, dfma<1>(Dt_G2G1, lap(G2PG1, g2pg1), g2pg1 + v3 + v6 - v7));
+        stq(SHP2, dfma<1>(Dt_S2, lap(SHP2, S2), S2 - v4 - v7));
+        stq(PG1S, dfma<1>(Dt_G1S2, lap(PG1S, pg1s), pg1s + v4 - v5));
+        stq(G2PG1S, dfma<1>(Dt_G2G1S2, lap(G2PG1S, g2pg1s), g2pg1s + v5 + v7));
+      }
+      if (mwarp) {
+        // ---- membrane fixed point on duals (tangent_kernel.cuh); exit decided by the values ----
+        const D1 m_old = x;
+        const D1 m_next = dshfl_down1<1>(m_old);
+        const D1 f = dfms<1>(m_old, dfma<1>(alpha2, m_old, alpha), beta * m_next);
+        const D1 fsrc = dshfl<1>(f, f_src);
+        D1 dm;
+        dm.v = fma(s_own, f.v, s_src * fsrc.v);
+        dm.p[0] = fma(s_own, f.p[0], s_src * fsrc.p[0]);
+        const D1 base = dfma<1>(dt, dm, m_old);
+        const D1 Md1 = dshfl<1>(m_old, src_den), Mn1 = dshfl<1>(m_old, src_num);
+        const D1 A_t = kf_t * Md1;
+        const D1 B_t = kr_t * Mn1;
+        __syncwarp();
+        D1 Iq = dconst<1>(0.0), Ii;
+        if (lane < NCY) { Iq.v = u_at(nxt, 0, lane, T - 2); Iq.p[0] = u_at(nxt, 1, lane, T - 2); }
+        Ii.v = u_at(nxt, 0, iSFK, T - 2); Ii.p[0] = u_at(nxt, 1, iSFK, T - 2);
+        const D1 cr = lane == aSFK ? dfma<1>(cf, Iq, ca * Ii) : cr_fixed;
+        int it = 0;
+        D1 Mn = Mn1, Md = Md1;
+        for (;;) {
+          ++it;
+          const D1 num = dfma<1>(cr, Mn, Iq);
+          D1 den = cf * Md;
+          den.v += 1.0;
+          const double rden = fast_recip(den.v);
+          D1 qv;
+          qv.v = num.v * rden;
+          qv.p[0] = fma(-qv.v, den.p[0], num.p[0]) * rden;
+          const D1 F = dfms<1>(A_t, qv, B_t);
+          const D1 F0 = dshfl<1>(F, fs0), F1 = dshfl<1>(F, fs1), F2 = dshfl<1>(F, fs2), F3 = dshfl<1>(F, fs3);
+          D1 mnew;
+          mnew.v = fma(sg0, F0.v, sg1 * F1.v) + fma(sg2, F2.v, fma(sg3, F3.v, base.v));
+          mnew.p[0] = fma(sg0, F0.p[0], sg1 * F1.p[0]) + fma(sg2, F2.p[0], fma(sg3, F3.p[0], base.p[0]));
+          const D1 xnew = lane < NCY ? qv : mnew;
+          const bool ok = (fabs(x.v - xnew.v) < tol * fabs(x.v)) || untracked;
+          x = xnew;
+          if (__all_sync(FULL, ok)) break;
+          if (it >= maxiters) break;
+          Mn = dshfl<1>(x, src_num);
+          Md = dshfl<1>(x, src_den);
+        }
+        bc_total += it;
+        if (lane < NCY) { u_at(nxt, 0, lane, T - 1) = x.v; u_at(nxt, 1, lane, T - 1) = x.p[0]; }
+      }
+      __syncthreads();
+      cur = nxt;
+      t = t + dt;
+      if (track_t && t.v >= t_save) {
+        if (nts >= Cn) status |= GAB1_ST_OVERFLOW;
+        else {
+          const int col = nts++;
+          publish_m();
+          __syncthreads();
+          if (a.o.out_mode == GAB1_OUT_FULL) write_column(col, cur);
+          else if (col == Cn - 1) {
+            for (int c = 0; c < 2; ++c) {
+              __syncthreads();
+              for (int n = tid; n < P; n += T) row[n] = stot_at(cur, c, n);
+              __syncthreads();
+              const double tr = trapz_r2(a.r, row, P);
+              if (c == 0) { pct_ave.v = tr; pct_memb.v = hdr[EG2PG1S]; } else { pct_ave.p[0] = tr; pct_memb.p[0] = hdr[16 + EG2PG1S]; }
+            }
+          }
+          __syncthreads();
+        }
+        t_save = t_save + a.o.dt_save;
+      }
+    }
+    publish_m();
+    __syncthreads();
+    const int fin = Nt == 0 ? 1 : cur;
+    bool ns = false;
+    if (a.o.out_mode == GAB1_OUT_FINAL4) {
+      for (int c = 0; c < 2; ++c) {
+        if (!ob[c]) continue;
+        for (int n = tid; n < P; n += T) {
+          const double v0 = at_node(fin, c, iSFK, n), v1 = at_node(fin, c, aSFK, n), v2 = ptot_at(fin, c, n), v3 = stot_at(fin, c, n);
+          ob[c][n] = v0; ob[c][P + n] = v1; ob[c][2 * P + n] = v2; ob[c][3 * P + n] = v3;
+          if (c == 0) ns |= isnan(v0) || isnan(v1) || isnan(v2) || isnan(v3);
+        }
+      }
+    } else if (a.o.out_mode == GAB1_OUT_FINAL_STATE) {
+      for (int c = 0; c < 2; ++c) {
+        if (!ob[c]) continue;
+        for (int q = 0; q < NCY; ++q)
+          for (int n = tid; n < P; n += T) { const double v = at_node(fin, c, q, n); ob[c][(long long)q * P + n] = v; if (c == 0) ns |= isnan(v); }
+        if (tid == 0)
+          for (int j = 0; j < NMB; ++j) { const double v = Nt == 0 ? 0.0 : hdr[16 * c + j]; ob[c][(long long)NCY * P + j] = v; if (c == 0) ns |= isnan(v); }
+      }
+    } else if (a.o.out_mode == GAB1_OUT_PCT_BOUND) {      // param_fitting+inference_finitediff.jl:211-216
+      const double R = a.o.R, R3 = R * R * R;
+      const double ave_v = pct_ave.v * 3.0 / R3, mem_v = pct_memb.v * a.o.pct_mul / a.o.pct_div;
+      const double pct_v = (ave_v + mem_v) / CoG1.v * 100.0;
+      ns |= isnan(pct_v);
+      if (lead && tid == 0) oset[0] = pct_v;
+      const double ave_p = pct_ave.p[0] * 3.0 / R3, mem_p = pct_memb.p[0] * a.o.pct_mul / a.o.pct_div;
+      if (tid == 0) ob[1][0] = ((ave_p + mem_p) / CoG1.v - ((ave_v + mem_v) / CoG1.v) * (CoG1.p[0] / CoG1.v)) * 100.0;
+    }
+    if (ns) status |= GAB1_ST_NAN;
+    if (track_t && nts < Cn) {
+      status |= GAB1_ST_SHORT;
+      if (a.o.out_mode == GAB1_OUT_FULL) {
+        for (int c = 0; c < 2; ++c) {
+          if (!ob[c]) continue;
+          long long o2 = 0;
+          for (int mi = 0; mi < 12; ++mi) {
+            if (!((a.o.matrix_mask >> mi) & 1u)) continue;
+            for (long long i = (long long)nts * P + tid; i < (long long)Cn * P; i += T) ob[c][o2 + i] = 0.0;
+            o2 += (long long)P * Cn;
+          }
+          for (int v = 0; v < GAB1_N_VECTORS; ++v)
+            for (int cc = nts + tid; cc < Cn; cc += T) ob[c][o2 + (long long)v * Cn + cc] = 0.0;
+        }
+      }
+    }
+    int st_all = 0;
+#pragma unroll
+    for (unsigned b = 1u; b <= GAB1_ST_THROW; b <<= 1)
+      if (__syncthreads_or((int)(status & b))) st_all |= (int)b;
+    if (lead && mwarp && lane == 0) {
+      if (a.status) a.status[set] = st_all;
+      if (a.n_saved) a.n_saved[set] = track_t ? nts : 0;
+      if (a.n_steps) a.n_steps[set] = Nt;
+      if (a.n_bc) a.n_bc[set] = bc_total;
+    }
+  }
+}
+
+}  // namespace gab1
