@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <atomic>
@@ -413,6 +414,7 @@ struct DeviceArena {
   size_t cap = 0;
 };
 static DeviceArena g_arena[64];
+static size_t& arena_prev_cap(int device) { static size_t prev[64] = {0}; return prev[device]; }
 
 // gab1_solve_ensemble_quantiles: the FULL result stays on the device and only order statistics come back
 struct QReq {
@@ -488,12 +490,22 @@ static int run_shard(const gab1_opts* o, int device, int64_t lo, int64_t hi, con
     oQ = take(nq * sizeof(double));
     oQws = take(gab1::quantiles_workspace_bytes(S) + 256);
   }
+  const bool dbg = getenv("GAB1_DEBUG_TIMING") != nullptr;
+  auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+  const double t_a = now();
   if (off > ar.cap) {
     if (ar.base) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(ar.base); ar.base = nullptr; ar.cap = 0; }
-    const size_t want = off + off / 8;
+    // cudaFree + cudaMalloc cost 20-500 ms on a 180 GB device (measured): start at 64 MB and at least double, so that a
+    // session of calls with growing batches re-allocates a handful of times at most
+    size_t want = off + off / 2;
+    if (want < ((size_t)64 << 20)) want = (size_t)64 << 20;
+    if (want < 2 * arena_prev_cap(device) && arena_prev_cap(device) <= ((size_t)4 << 30)) want = 2 * arena_prev_cap(device);
     CUDA_TRY(cudaMalloc((void**)&ar.base, want));
     ar.cap = want;
+    arena_prev_cap(device) = want;
   }
+  const double t_b = now();
+  if (dbg) fprintf(stderr, "[gab1] run_shard S=%lld arena %.1f ms (cap %zu)\n", (long long)S, 1e3 * (t_b - t_a), ar.cap);
   double *dCo = (double*)(ar.base + oCo), *dD = (double*)(ar.base + oD), *dk = (double*)(ar.base + oK),
          *ddt = (double*)(ar.base + oDt), *dr_ = (double*)(ar.base + oR), *dout = (double*)(ar.base + oOut);
   int32_t *dstatus = (int32_t*)(ar.base + oSt), *dsaved = (int32_t*)(ar.base + oSv);
@@ -504,11 +516,14 @@ static int run_shard(const gab1_opts* o, int device, int64_t lo, int64_t hi, con
   CUDA_TRY(cudaMemcpyAsync(dk, k + lo * GAB1_N_K, (size_t)S * GAB1_N_K * sizeof(double), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(ddt, dt + lo, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(dr_, r, P * sizeof(double), cudaMemcpyHostToDevice, st));
+  const double t_c = now();
   if (int e = solve_device(o, device, st, S, dCo, Co_stride, dD, dk, ddt, dr_, out_direct ? out_direct : dout, dstatus, dsaved,
                            (long long*)dsteps, (long long*)dbc, ws)) {
     cudaStreamSynchronize(st);
     return e;
   }
+  if (dbg) { const double t_d = now(); cudaStreamSynchronize(st);
+    fprintf(stderr, "[gab1] run_shard S=%lld enqueue %.1f ms, kernels %.1f ms\n", (long long)S, 1e3 * (t_d - t_c), 1e3 * (now() - t_d)); }
   if (qr) {
     double* dq = (double*)(ar.base + oQ);
     long long* dnv = (long long*)(ar.base + oQws);
@@ -582,9 +597,12 @@ static int run_tangent_shard(const gab1_opts* o, int device, int64_t lo, int64_t
                oOut = take((size_t)S * nout * sizeof(double));
   if (off > ar.cap) {
     if (ar.base) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(ar.base); ar.base = nullptr; ar.cap = 0; }
-    const size_t want = off + off / 8;
+    size_t want = off + off / 2;
+    if (want < ((size_t)64 << 20)) want = (size_t)64 << 20;
+    if (want < 2 * arena_prev_cap(device) && arena_prev_cap(device) <= ((size_t)4 << 30)) want = 2 * arena_prev_cap(device);
     CUDA_TRY(cudaMalloc((void**)&ar.base, want));
     ar.cap = want;
+    arena_prev_cap(device) = want;
   }
   double *dCo = (double*)(ar.base + oCo), *dD = (double*)(ar.base + oD), *dk = (double*)(ar.base + oK),
          *ddt = (double*)(ar.base + oDt), *dsd = (double*)(ar.base + oSd), *dr_ = (double*)(ar.base + oR),
@@ -707,6 +725,7 @@ void gab1_release_device_memory(void) {
     if (cudaSetDevice(d) != cudaSuccess) continue;
     if (ar.stream) { cudaStreamSynchronize(ar.stream); cudaStreamDestroy(ar.stream); ar.stream = nullptr; }
     if (ar.base) { cudaFree(ar.base); ar.base = nullptr; ar.cap = 0; }
+    arena_prev_cap(d) = 0;
   }
 }
 
