@@ -396,3 +396,26 @@ def test_runs_are_bitwise_repeatable(pkg, gfe, ensemble, family, monkeypatch):
         b = gfe.pdesolver_batch(Co, ensemble[sub, :7], ensemble[sub, 7:], **kw)
         assert_bits(a.out, b.out, f"{family or 'default'} dr={dr}")
         check_control_flow(a, b)
+
+
+@pytest.mark.parametrize("family", ["legacy", "group16", "group32", "stream", "team"])
+def test_blow_up_takes_the_dead_state_path_in_every_family(pkg, gfe, ofe, ensemble, family, monkeypatch):
+    """A time step 2.5x the stability limit blows every set up within a few hundred steps: values overflow, turn NaN, and the
+    kernels' all-NaN fast-forward (clock and snapshot schedule only) takes over.  Status words, step counts, snapshot counts
+    and the final column must be what the oracle produces by brute force."""
+    monkeypatch.setenv("GAB1_KERNEL", family)
+    Co = pkg.params.base_Co()
+    rows = [0, 1, 2, 3, 4999]
+    D, k = ensemble[rows, :7], ensemble[rows, 7:]
+    for dr in {"legacy": (0.2, 0.1), "group16": (0.4, 0.2), "group32": (0.2, 0.05), "stream": (0.2, 0.05, 0.025), "team": (0.1, 0.05)}[family]:
+        dt = 2.5 * pkg.params.default_dt(D, k, dr)
+        kw = dict(dr=dr, tf=3000 * float(dt.max()), Nts=6, dt=dt, tol=1e-4, maxiters=20)
+        res = gfe.pdesolver_batch(Co, D, k, **kw)
+        ref = ofe.pdesolver_batch(Co, D, k, **kw)
+        assert np.all(ref.status & pkg.abi.ST_NAN), "the oracle did not blow up: the test is not testing anything"
+        np.testing.assert_array_equal(res.status, ref.status)
+        np.testing.assert_array_equal(res.n_steps, ref.n_steps)
+        np.testing.assert_array_equal(res.n_saved, ref.n_saved)
+        last_g, last_r = res.matrix("PG1S")[:, :, -1], ref.matrix("PG1S")[:, :, -1]
+        np.testing.assert_array_equal(np.isnan(last_g), np.isnan(last_r))
+        np.testing.assert_array_equal(res.vector("t_out"), ref.vector("t_out"))
