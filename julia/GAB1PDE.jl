@@ -125,6 +125,18 @@ function ensemble_quantiles(ensemble, Co; probs=(:median, 0.5 - 0.341, 0.5 + 0.3
     Dict(name => q[:, :, :, i] for (i, name) in enumerate(order)), nv[1], r, status
 end
 
+"`linear_interpolation(r, y)(0:dr_new:R)` along the node axis (first dimension): the re-gridding of run_base_model.jl:108-119"
+function regrid(values::AbstractArray, r::AbstractVector; dr_new=0.1, R=10.0)
+    x = collect(0.0:dr_new:R)
+    out = similar(values, Float64, (length(x), size(values)[2:end]...))
+    for (j, xj) in enumerate(x)
+        i = clamp(searchsortedlast(r, xj), 1, length(r) - 1)
+        w = (xj - r[i]) / (r[i+1] - r[i])
+        selectdim(out, 1, j) .= (1 - w) .* selectdim(values, 1, i) .+ w .* selectdim(values, 1, i + 1)
+    end
+    out, x
+end
+
 ## ---------------------------------------------------------------- single solves, reference names
 function _sol(b::Batch, j; extra=false, ncol=b.o.Nts + 1)
     mats = NamedTuple{MATRICES}(Tuple(matrix(b, n, j)[:, 1:ncol] for n in MATRICES))

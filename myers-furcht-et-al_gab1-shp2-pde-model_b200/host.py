@@ -137,6 +137,20 @@ class Frontend:
         order = sorted(matrices, key=abi.MATRIX_NAMES.index)
         return {name: q[i] for i, name in enumerate(order)}, n_valid, r, status
 
+    @staticmethod
+    def regrid(values, r, dr_new=0.1, R=10.0):
+        """`linear_interpolation(r, y)(0:dr_new:R)` along the node axis (the last one) — the re-gridding run_base_model.jl
+        applies to the summary surfaces (:108-119, 134-145, 161-172).  A host-side operation on the ~0.5 MB of statistics
+        ensemble_quantiles returns.  Interpolations.jl is not in the reference tree: its linear rule is restated as
+        (1 - w) * y[i] + w * y[i+1] with w = (x - r[i]) / (r[i+1] - r[i]) (unpinned in the last bit).
+        Returns (values on the new grid, the new grid)."""
+        r = np.asarray(r, dtype=np.float64)
+        x = params.julia_range(dr_new, R)
+        i = np.clip(np.searchsorted(r, x, side="right") - 1, 0, len(r) - 2)
+        w = (x - r[i]) / (r[i + 1] - r[i])
+        v = np.asarray(values, dtype=np.float64)
+        return (1.0 - w) * v[..., i] + w * v[..., i + 1], x
+
     def _run(self, o, Co, Dmat, kmat, dt, dr, r) -> BatchResult:
         Dmat = np.ascontiguousarray(Dmat, dtype=np.float64).reshape(-1, abi.N_D)
         kmat = np.ascontiguousarray(kmat, dtype=np.float64).reshape(-1, abi.N_K)

@@ -75,3 +75,14 @@ def test_gpu_quantiles_of_the_whole_ensemble_are_ordered(pkg, ensemble):
     for name, q in res.items():
         assert q.shape == (3, 11, 51) and np.isfinite(q).all()
         assert (q[0] <= q[1]).all() and (q[1] <= q[2]).all()
+
+
+def test_regrid_is_piecewise_linear_interpolation(pkg):
+    """run_base_model.jl:108-119: summary surfaces interpolated from the dr = 0.2 grid onto 0:0.1:R."""
+    r = pkg.params.julia_range(0.2, 10.0)
+    y = np.stack([np.sin(r), r ** 2])                       # (2, 51)
+    v, x = pkg.host.Frontend.regrid(y, r, dr_new=0.1, R=10.0)
+    assert v.shape == (2, 101) and np.array_equal(x, pkg.params.julia_range(0.1, 10.0))
+    np.testing.assert_array_equal(v[:, ::2], y)             # knots are reproduced exactly
+    np.testing.assert_allclose(v[:, 1::2], 0.5 * (y[:, :-1] + y[:, 1:]), rtol=1e-13, atol=1e-15)    # midpoints (w = 0.5 up to the rounding of x - r[i])
+    np.testing.assert_allclose(v, np.stack([np.interp(x, r, y[0]), np.interp(x, r, y[1])]), rtol=1e-13, atol=1e-15)
