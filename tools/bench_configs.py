@@ -24,7 +24,7 @@ sys.path.insert(0, str(ROOT))
 PKG = "myers-furcht-et-al_gab1-shp2-pde-model_b200"
 
 
-def configs(pkg, scale):
+def configs(pkg, scale, cap=1_000_000):
     abi, params = pkg.abi, pkg.params
     ens = params.load_parameter_ensemble()
     out = {}
@@ -41,9 +41,9 @@ def configs(pkg, scale):
     # 4: sapdesolver_membSFK with HeLa concentrations
     S4 = int(100000 * scale)
     e4 = params.resampled_ensemble(S4, seed=123)
-    o4 = abi.make_opts(dr=0.2, Nts=1, tol=1e-3, maxiters=1_000_000, out_mode=abi.OUT_FINAL4, sfk_mode=abi.SFK_MEMBRANE,
+    o4 = abi.make_opts(dr=0.2, Nts=1, tol=1e-3, maxiters=cap, out_mode=abi.OUT_FINAL4, sfk_mode=abi.SFK_MEMBRANE,
                        bc_loop=abi.BC_WHILE, pg1tot_form=abi.PG1TOT_CHAIN)
-    out[4] = dict(name=f"configs[3]: sapdesolver_membSFK, HeLa concentrations, {S4} resampled sets, dr=0.2, tol=1e-3",
+    out[4] = dict(name=f"configs[3]: sapdesolver_membSFK, HeLa concentrations, {S4} resampled sets, dr=0.2, tol=1e-3, while-loop cap {cap}",
                   o=o4, Co=params.hela_Co(), D=e4[:, :7], k=e4[:, 7:], dr=0.2, f_int=229.0)
     # 5: rectangular geometry at 4x refinement
     S5 = max(2, int(1184 * scale))
@@ -59,6 +59,7 @@ def main():
     ap.add_argument("--configs", default="1,3,4,5")
     ap.add_argument("--scale", type=float, default=1.0, help="scale the ensemble sizes (quick runs)")
     ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--cap", type=int, default=1_000_000, help="configs[3]: safety cap of the `while error > tol` loop (wrappers default: 100000)")
     ap.add_argument("--tf", type=float, default=None, help="profiling runs only: a shorter final time than the configs' tf = 5")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
@@ -71,7 +72,7 @@ def main():
     assert lib.gab1_device_count() >= args.devices, "not enough CUDA devices"
     peak = lib.gab1_measure_fp64_tflops(0, 0.5)
     dp, ip, lp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
-    cfgs = configs(pkg, args.scale)
+    cfgs = configs(pkg, args.scale, args.cap)
     for ci in [int(x) for x in args.configs.split(",")]:
         if ci == 2:
             # configs[1] reduced on the device: median surface and the +-1 sigma band of three matrices over all snapshots
