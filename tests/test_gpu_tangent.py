@@ -289,3 +289,17 @@ def test_team_tangent_kernel(pkg, gfe, ofe, ensemble, mode, monkeypatch):
                 check(res, ref, abi, (Co, D, k))
             except AssertionError as e:
                 raise AssertionError(f"{family} dr={dr}: {e}") from e
+
+
+def test_fitting_gradient_full_length_final_stage_grid(pkg, gfe, ofe):
+    """The final optimisation stage of the reference runs at dr = 0.1 (param_fitting+inference_finitediff.jl:240,263): two
+    full-length (tf = 5, 1.4e5 steps) loss-and-gradient evaluations through the default dispatch (one CTA per set and
+    direction) against the dual oracle."""
+    p0 = np.concatenate([pkg.params.DIFFS_BASE, pkg.params.KVALS_BASE])
+    inds = [7 + j for j in FIT_K]
+    x = np.log(p0[inds])[None, :] + np.array([[0.0, 0.0, 0.0, 0.0], [0.4, -0.3, 0.2, -0.5]])
+    kw = dict(param_inds=inds, pvals0=p0, Co=pkg.params.base_Co(), dr=0.1, tf=5.0, Nts=100, tol=1e-3, maxiters=20)
+    lg, gg, yg = gfe.fitting_loss_and_gradient(x, 26.426, 9.363, **kw)
+    lo, go, yo = ofe.fitting_loss_and_gradient(x, 26.426, 9.363, **kw)
+    assert np.abs(yg / yo - 1).max() < RTOL
+    assert np.abs(gg - go).max() <= 1e-8 * np.abs(go).max()
