@@ -291,11 +291,12 @@ int solve_tangent_device(const gab1_opts* o, int device, cudaStream_t stream, lo
   }
   // one CTA per (set, direction) while every one of them is resident (team_tangent_kernel.cuh; measured in DESIGN.md section 8)
   bool team = false;
-  if (o->Nr > 64 && o->Nr <= 256) {
+  if (o->Nr > 32 && o->Nr <= 256) {
     int nsm = 148;
     (void)cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
     // dr = 0.1, one / 37 / 101 evaluations with 4 partials: 127 / 138 / 309 ms against 577 / 628 / 654 ms for one warp per
-    // (set, direction); two CTAs are resident per SM, so 8 * SMs items are four rounds of ~130 ms
+    // (set, direction); two CTAs are resident per SM, so 8 * SMs items are four rounds of ~130 ms.
+    // dr = 0.2 (teams of 2 warps): 1 / 37 / 101 / 296 evaluations 33 / 37 / 116 / 139 ms against 60 / 67 / 168 / 185 ms
     team = S * (long long)n_dir <= 8LL * nsm;
     if (const char* e = getenv("GAB1_TANGENT")) { if (strcmp(e, "team") == 0) team = true; else if (e[0]) team = false; }
   }

@@ -6,6 +6,7 @@
 // team_kernel.cuh carries a dual number per node: value and ONE partial of all ten species as a ping-pong pair in
 // shared memory, thread t = node t, the last warp runs the lane-parallel fixed point on duals (tangent_kernel.cuh),
 // one __syncthreads() per step.  The four directions of a gradient are four CTAs.
+// Measured: one gradient (4 partials) 127 ms at dr = 0.1, 33 ms at dr = 0.2 (one warp per pair: 577 and 60 ms).
 // Same restrictions as gab1_solve_tangent; arithmetic forms as tangent_kernel.cuh.
 #pragma once
 #include "tangent_kernel.cuh"
