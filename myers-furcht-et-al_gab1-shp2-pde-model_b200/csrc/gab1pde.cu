@@ -297,7 +297,10 @@ int solve_tangent_device(const gab1_opts* o, int device, cudaStream_t stream, lo
     // dr = 0.1, one / 37 / 101 evaluations with 4 partials: 127 / 138 / 309 ms against 577 / 628 / 654 ms for one warp per
     // (set, direction); two CTAs are resident per SM, so 8 * SMs items are four rounds of ~130 ms.
     // dr = 0.2 (teams of 2 warps): 1 / 37 / 101 / 296 evaluations 33 / 37 / 116 / 139 ms against 60 / 67 / 168 / 185 ms
-    team = S * (long long)n_dir <= 8LL * nsm;
+    // full-size batches: dr = 0.1, 1184 sets x 4 partials 2.55 s (11.5x a primal solve) against 3.6 s streamed (16.2x): the
+    // team kernel serves 64 < Nr <= 128 at every batch size; dr = 0.2, 4736 sets: 1.48 s against 1.19 s for the register
+    // kernel with two directions per item, which keeps the large batches there
+    team = o->Nr > 64 || S * (long long)n_dir <= 8LL * nsm;
     if (const char* e = getenv("GAB1_TANGENT")) { if (strcmp(e, "team") == 0) team = true; else if (e[0]) team = false; }
   }
   ta.groups = (n_dir + NT - 1) / NT;
