@@ -313,7 +313,16 @@ int solve_tangent_device(const gab1_opts* o, int device, cudaStream_t stream, lo
   size_t bytes = w.cub_bytes;
   CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp, bytes, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)S,
                                                      0, 32, stream));
-  if (team) return gab1::launch_team_tangent_kernel(ta, device, stream);
+  if (team) {
+    // directions per CTA: two share one primal (dr = 0.1, 1184 sets x 4 partials: 2.02 s against 2.62 s with one) once the batch
+    // fills the GPU; one per CTA is the latency optimum (one gradient: 127 vs 205 ms).  dr = 0.2: no difference at full size.
+    int nsm = 148;
+    (void)cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+    int NTt = (n_dir >= 2 && o->Nr > 64 && S * (long long)n_dir > 8LL * nsm) ? 2 : 1;
+    if (const char* e = getenv("GAB1_TANGENT_NT")) { const int v = atoi(e); if (v == 1 || (v == 2 && n_dir >= 2)) NTt = v; }
+    ta.groups = (n_dir + NTt - 1) / NTt;
+    return gab1::launch_team_tangent_kernel(NTt, ta, device, stream);
+  }
   return streamed ? gab1::launch_tangent_stream_kernel(K, NT, ta, device, stream)
                   : gab1::launch_tangent_kernel(K, NT, ta, device, stream);
 }

@@ -61,7 +61,7 @@ struct TangentArgs {
 int tangent_directions_per_item(int K, int n_dir);
 int launch_tangent_kernel(int K, int NT, const TangentArgs& ta, int device, cudaStream_t stream);
 // latency path of forward mode (team_tangent_kernel.cuh): one CTA per (set, direction), 64 < Nr <= 256
-int launch_team_tangent_kernel(const TangentArgs& ta, int device, cudaStream_t stream);
+int launch_team_tangent_kernel(int NT, const TangentArgs& ta, int device, cudaStream_t stream);
 // streamed-partials kernels (tangent_stream_kernel.cuh): primal in registers, partials in shared memory; NT in {2, 4}
 int launch_tangent_stream_kernel(int K, int NT, const TangentArgs& ta, int device, cudaStream_t stream);
 // synthetic prior ensembles on the device (sampler.cu); mu, sigma are host pointers

@@ -13,9 +13,11 @@
 
 namespace gab1 {
 
+template <int NT>
 __global__ void __launch_bounds__(256)
 team_tangent_kernel(const TangentArgs ta) {
-  typedef Dn<1> D1;
+  typedef Dn<NT> D1;
+  constexpr int NC = 1 + NT;                           // components: value, NT partials
   const KernelArgs& a = ta.a;
   extern __shared__ double smem[];
   __shared__ unsigned s_item;
@@ -24,10 +26,10 @@ team_tangent_kernel(const TangentArgs ta) {
   const int Nr = a.o.Nr, P = Nr + 1, Nts = a.o.Nts, Cn = Nts + 1;
   const int off = Nr - (T - 1);
   const int node = tid + off;
-  double* U = smem;                                    // [2 buffers][2 components][NCY][T]
-  double* hdr = smem + 4 * NCY * T;                    // [0,16): membrane values, [16,32): their partials
-  double* row = hdr + WS_HDR;                          // P_pad doubles
-  auto u_at = [&](int buf, int c, int q, int slot) -> double& { return U[((buf * 2 + c) * NCY + q) * T + slot]; };
+  double* U = smem;                                    // [2 buffers][NC components][NCY][T]
+  double* hdr = smem + 2 * NC * NCY * T;               // [16 c, 16 c + 8): membrane values of component c
+  double* row = hdr + 16 * NC;                         // P_pad doubles
+  auto u_at = [&](int buf, int c, int q, int slot) -> double& { return U[((buf * NC + c) * NCY + q) * T + slot]; };
 
   const bool interior = node >= 1 && node <= Nr - 1;
   double cpc = 0.0, cmc = 0.0, c0c = 0.0;
@@ -40,7 +42,7 @@ team_tangent_kernel(const TangentArgs ta) {
     if (interior) { cpc = cp; cmc = cm; c0c = c0; }
   }
   const int sl = tid > 0 ? tid - 1 : 0, sr = tid < T - 1 ? tid + 1 : T - 1;
-  const long long items = a.S * (long long)ta.n_dir;
+  const long long items = a.S * (long long)ta.groups;
 
   for (;;) {
     __syncthreads();
@@ -48,32 +50,51 @@ team_tangent_kernel(const TangentArgs ta) {
     __syncthreads();
     const unsigned item = s_item;
     if ((long long)item >= items) break;
-    const long long si = item / ta.n_dir;
-    const int dir = (int)(item - si * ta.n_dir);
+    const long long si = item / ta.groups;
+    const int group = (int)(item - si * ta.groups);
     const long long set = a.order ? (long long)a.order[si] : si;
-    const bool lead = dir == 0;                          // owns the value block and the diagnostics
+    const bool lead = group == 0;                        // owns the value block and the diagnostics
 
     const long long nout = a.out_stride;
     double* oset = a.out + set * nout * (1 + ta.n_dir);
-    double* ob[2] = {lead ? oset : nullptr, oset + (long long)(1 + dir) * nout};
+    double* ob[NC];
+    const double* sd[NT];
+    ob[0] = lead ? oset : nullptr;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const int d = group * NT + n;
+      ob[1 + n] = d < ta.n_dir ? oset + (long long)(1 + d) * nout : nullptr;
+      sd[n] = d < ta.n_dir ? ta.seeds + (set * ta.n_dir + d) * GAB1_N_SEED : nullptr;
+    }
+    auto seed = [&](int n, int i) -> double { return sd[n] ? sd[n][i] : 0.0; };
     unsigned status = 0;
     const double* Cov = a.Co + set * a.Co_stride;
     const double* Dv = a.D + set * GAB1_N_D;
     const double* kv = a.k + set * GAB1_N_K;
-    const double* sd = ta.seeds + (set * ta.n_dir + dir) * GAB1_N_SEED;
-    auto Dd = [&](int i) { D1 r; r.v = Dv[i]; r.p[0] = sd[i]; return r; };
-    auto kd = [&](int i) { D1 r; r.v = kv[i]; r.p[0] = sd[GAB1_N_D + i]; return r; };
-    auto Cod = [&](int i) { D1 r; r.v = Cov[i]; r.p[0] = sd[GAB1_N_D + GAB1_N_K + i]; return r; };
-    D1 dt; dt.v = a.dt[set]; dt.p[0] = sd[GAB1_N_SEED - 1];
+    auto Dd = [&](int i) { D1 r; r.v = Dv[i];
+#pragma unroll
+      for (int n = 0; n < NT; ++n) r.p[n] = seed(n, i); return r; };
+    auto kd = [&](int i) { D1 r; r.v = kv[i];
+#pragma unroll
+      for (int n = 0; n < NT; ++n) r.p[n] = seed(n, GAB1_N_D + i); return r; };
+    auto Cod = [&](int i) { D1 r; r.v = Cov[i];
+#pragma unroll
+      for (int n = 0; n < NT; ++n) r.p[n] = seed(n, GAB1_N_D + GAB1_N_K + i); return r; };
+    D1 dt; dt.v = a.dt[set];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) dt.p[n] = seed(n, GAB1_N_SEED - 1);
+    auto comp_of = [&](const D1& x, int c) { double v = x.v;
+#pragma unroll
+      for (int n = 0; n < NT; ++n) if (c == n + 1) v = x.p[n]; return v; };
     const D1 CoSFK = Cod(0), CoG2 = Cod(1), CoG1 = Cod(2), CoS2 = Cod(3), CoEGFR = Cod(4);
     D1 D_Si = Dd(0), D_Sa = Dd(0);
-    if (a.o.sfk_mode == GAB1_SFK_MEMBRANE) D_Sa = dconst<1>(1e-32);
-    if (a.o.sfk_mode == GAB1_SFK_BOTH_FROZEN) { D_Si = dconst<1>(1e-32); D_Sa = dconst<1>(1e-32); }
+    if (a.o.sfk_mode == GAB1_SFK_MEMBRANE) D_Sa = dconst<NT>(1e-32);
+    if (a.o.sfk_mode == GAB1_SFK_BOTH_FROZEN) { D_Si = dconst<NT>(1e-32); D_Sa = dconst<NT>(1e-32); }
     const bool track_t = (a.o.out_mode == GAB1_OUT_FULL || a.o.out_mode == GAB1_OUT_PCT_BOUND);
 
     const double nt_f = ceil(__ddiv_rn(a.o.tf, dt.v));
     if (!(nt_f >= 0.0 && nt_f < 9.0e18)) {
-      for (int c = 0; c < 2; ++c)
+      for (int c = 0; c < NC; ++c)
         if (ob[c]) for (long long i = tid; i < nout; i += T) ob[c][i] = 0.0;
       if (lead && tid == 0) {
         if (a.status) a.status[set] = GAB1_ST_THROW;
@@ -88,12 +109,17 @@ team_tangent_kernel(const TangentArgs ta) {
     {
       const bool on = node >= 1 && node <= Nr;
 #pragma unroll
-      for (int q = 0; q < NCY; ++q) { u_at(0, 0, q, tid) = 0.0; u_at(0, 1, q, tid) = 0.0; u_at(1, 0, q, tid) = 0.0; u_at(1, 1, q, tid) = 0.0; }
-      u_at(0, 0, iSFK, tid) = on ? CoSFK.v : 0.0; u_at(0, 1, iSFK, tid) = on ? CoSFK.p[0] : 0.0;
-      u_at(0, 0, GAB1, tid) = on ? CoG1.v : 0.0;  u_at(0, 1, GAB1, tid) = on ? CoG1.p[0] : 0.0;
-      u_at(0, 0, GRB2, tid) = on ? CoG2.v : 0.0;  u_at(0, 1, GRB2, tid) = on ? CoG2.p[0] : 0.0;
-      u_at(0, 0, SHP2, tid) = on ? CoS2.v : 0.0;  u_at(0, 1, SHP2, tid) = on ? CoS2.p[0] : 0.0;
-      if (tid < WS_HDR) hdr[tid] = 0.0;
+      for (int q = 0; q < NCY; ++q)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { u_at(0, c, q, tid) = 0.0; u_at(1, c, q, tid) = 0.0; }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        u_at(0, c, iSFK, tid) = on ? comp_of(CoSFK, c) : 0.0;
+        u_at(0, c, GAB1, tid) = on ? comp_of(CoG1, c) : 0.0;
+        u_at(0, c, GRB2, tid) = on ? comp_of(CoG2, c) : 0.0;
+        u_at(0, c, SHP2, tid) = on ? comp_of(CoS2, c) : 0.0;
+      }
+      if (tid < 16 * NC) hdr[tid] = 0.0;
     }
     __syncthreads();                                     // the initial state is visible to the neighbours
     int cur = 0;
@@ -106,9 +132,9 @@ team_tangent_kernel(const TangentArgs ta) {
     };
 
     if (a.o.out_mode == GAB1_OUT_FULL) {
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < NC; ++c) {
         if (!ob[c]) continue;
-        auto comp = [&](const D1& x) { return c == 0 ? x.v : x.p[0]; };
+        auto comp = [&](const D1& x) { return comp_of(x, c); };
         long long o2 = 0;
         for (int mi = 0; mi < 12; ++mi) {
           if (!((a.o.matrix_mask >> mi) & 1u)) continue;
@@ -121,11 +147,11 @@ team_tangent_kernel(const TangentArgs ta) {
       }
     }
 
-    D1 t = dconst<1>(0.0);
+    D1 t = dconst<NT>(0.0);
     double t_save = a.o.dt_save;
     int nts = 1;
     long long bc_total = 0;
-    D1 pct_ave = dconst<1>(0.0), pct_memb = dconst<1>(0.0);
+    D1 pct_ave = dconst<NT>(0.0), pct_memb = dconst<NT>(0.0);
 
     const D1 kS2f_t = kd(0) * dt, kS2r_t = kd(1) * dt, kG1f_t = kd(2) * dt, kG1r_t = kd(3) * dt, kG1p_t = kd(6) * dt,
              kG1dp_t = kd(7) * dt, kSi_t = kd(9) * dt;
@@ -134,7 +160,7 @@ team_tangent_kernel(const TangentArgs ta) {
 
     // ---- membrane block: lane roles of the last warp (tangent_kernel.cuh) ----
     constexpr int LZ = 31, LE = ML + NMB;
-    D1 kf = dconst<1>(0.0), kr = dconst<1>(0.0), Dq = dconst<1>(1.0);
+    D1 kf = dconst<NT>(0.0), kr = dconst<NT>(0.0), Dq = dconst<NT>(1.0);
     int src_num = LZ, src_den = LZ;
     switch (lane) {
       case iSFK:   kf = kd(8); Dq = D_Si; src_den = LE; break;
@@ -149,12 +175,12 @@ team_tangent_kernel(const TangentArgs ta) {
       case G2PG1S: kf = kd(4); kr = kd(5); Dq = Dd(3); src_num = ML + EG2PG1S; src_den = ML + E;      break;
       default: break;
     }
-    const D1 drD = drdiv<1>(a.o.dr, Dq);
+    const D1 drD = drdiv<NT>(a.o.dr, Dq);
     const D1 cf = kf * drD;
     const D1 cr_fixed = kr * drD;
-    const D1 ca = kd(8) * drdiv<1>(a.o.dr, D_Sa);
+    const D1 ca = kd(8) * drdiv<NT>(a.o.dr, D_Sa);
     const bool is_flux = lane >= GAB1 && lane <= G2PG1S;
-    const D1 kf_t = is_flux ? kf * dt : dconst<1>(0.0), kr_t = is_flux ? kr * dt : dconst<1>(0.0);
+    const D1 kf_t = is_flux ? kf * dt : dconst<NT>(0.0), kr_t = is_flux ? kr * dt : dconst<NT>(0.0);
     int fs0 = LZ, fs1 = LZ, fs2 = LZ, fs3 = LZ;
     double sg0 = 0.0, sg1 = 0.0, sg2 = 0.0, sg3 = 0.0;
     switch (lane - ML) {
@@ -165,7 +191,7 @@ team_tangent_kernel(const TangentArgs ta) {
       case EG2PG1S: fs0 = G2PG1S; fs1 = PG1S;  fs2 = SHP2; sg0 = 1.0; sg1 = 1.0; sg2 = 1.0; break;
       default: break;
     }
-    D1 alpha = dconst<1>(0.0), alpha2 = dconst<1>(0.0), beta = dconst<1>(0.0);
+    D1 alpha = dconst<NT>(0.0), alpha2 = dconst<NT>(0.0), beta = dconst<NT>(0.0);
     double s_own = 0.0, s_src = 0.0;
     int f_src = LZ;
     switch (lane - ML) {
@@ -179,13 +205,18 @@ team_tangent_kernel(const TangentArgs ta) {
     const double tol = a.o.tol;
     const bool untracked = lane >= LE;
     const int maxiters = a.o.maxiters;
-    D1 x = (lane == ML + mE) ? CoEGFR : dconst<1>(0.0);
+    D1 x = (lane == ML + mE) ? CoEGFR : dconst<NT>(0.0);
 
-    auto publish_m = [&]() { if (mwarp && lane >= ML && lane < LE) { hdr[lane - ML] = x.v; hdr[16 + lane - ML] = x.p[0]; } };
+    auto publish_m = [&]() {
+      if (mwarp && lane >= ML && lane < LE) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) hdr[16 * c + lane - ML] = comp_of(x, c);
+      }
+    };
     // one snapshot column, both components; hdr holds the membrane values (after publish_m + __syncthreads)
     auto write_column = [&](int col, int b) {
       constexpr int kSpecies[10] = {iSFK, aSFK, GRB2, GAB1, SHP2, G2G1, G2PG1, G2PG1S, pGAB1, PG1S};
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < NC; ++c) {
         if (!ob[c]) continue;
         long long o2 = 0;
         for (int mi = 0; mi < 12; ++mi) {
@@ -205,10 +236,10 @@ team_tangent_kernel(const TangentArgs ta) {
           } else {                                             // quotient rule for the two outputs that divide by CoEGFR
             const double* mv = hdr;
             const double Etot_v = 2.0 * (mv[E] + mv[EG2] + mv[EG2G1] + mv[EG2PG1] + mv[EG2PG1S]);
-            const double w = CoEGFR.p[0] / CoEGFR.v;
+            const double w = comp_of(CoEGFR, c) / CoEGFR.v;
             v[GAB1_V_pE * (long long)Cn + col] = (Etot * 100.0) / CoEGFR.v - (Etot_v * 100.0 / CoEGFR.v) * w;
             v[GAB1_V_EGFR_SHP2 * (long long)Cn + col] = (m[EG2PG1S] * 100.0) / CoEGFR.v - (mv[EG2PG1S] * 100.0 / CoEGFR.v) * w;
-            v[GAB1_V_t_out * (long long)Cn + col] = t.p[0];
+            v[GAB1_V_t_out * (long long)Cn + col] = comp_of(t, c);
           }
           v[GAB1_V_mE * (long long)Cn + col] = m[mE];
           v[GAB1_V_mES * (long long)Cn + col] = m[mES];
@@ -229,81 +260,95 @@ team_tangent_kernel(const TangentArgs ta) {
       const int nxt = cur ^ 1;
       // ---- interior on duals: thread = node, old buffer -> new buffer ----
       {
-        auto ldq = [&](int q, int slot) { D1 r; r.v = u_at(cur, 0, q, slot); r.p[0] = u_at(cur, 1, q, slot); return r; };
+        auto ldq = [&](int q, int slot) { D1 r; r.v = u_at(cur, 0, q, slot);
+#pragma unroll
+          for (int n = 0; n < NT; ++n) r.p[n] = u_at(cur, 1 + n, q, slot); return r; };
         const D1 Si = ldq(iSFK, tid), Sa = ldq(aSFK, tid), G1 = ldq(GAB1, tid), pG1 = ldq(pGAB1, tid), G2 = ldq(GRB2, tid),
                  g2g1 = ldq(G2G1, tid), g2pg1 = ldq(G2PG1, tid), S2 = ldq(SHP2, tid), pg1s = ldq(PG1S, tid), g2pg1s = ldq(G2PG1S, tid);
         auto lap = [&](int q, const D1& uc) {
           const D1 up = ldq(q, sr), um = ldq(q, sl);
           D1 r;
           r.v = fma(cpc, up.v, fma(cmc, um.v, c0c * uc.v));
-          r.p[0] = fma(cpc, up.p[0], fma(cmc, um.p[0], c0c * uc.p[0]));
+#pragma unroll
+          for (int n = 0; n < NT; ++n) r.p[n] = fma(cpc, up.p[n], fma(cmc, um.p[n], c0c * uc.p[n]));
           return r;
         };
-        auto stq = [&](int q, const D1& val) { u_at(nxt, 0, q, tid) = val.v; u_at(nxt, 1, q, tid) = val.p[0]; };
+        auto stq = [&](int q, const D1& val) { u_at(nxt, 0, q, tid) = val.v;
+#pragma unroll
+          for (int n = 0; n < NT; ++n) u_at(nxt, 1 + n, q, tid) = val.p[n]; };
         const D1 gb = kG1f_t * G2, ph = kG1p_t * Sa, sb = kS2f_t * S2;
-        const D1 v1 = dfms<1>(gb, G1, kG1r_t * g2g1);
-        const D1 v3 = dfms<1>(gb, pG1, kG1r_t * g2pg1);
-        const D1 v5 = dfms<1>(gb, pg1s, kG1r_t * g2pg1s);
-        const D1 v2 = dfms<1>(ph, G1, kG1dp_t * pG1);
-        const D1 v6 = dfms<1>(ph, g2g1, kG1dp_t * g2pg1);
-        const D1 v4 = dfms<1>(sb, pG1, kS2r_t * pg1s);
-        const D1 v7 = dfms<1>(sb, g2pg1, kS2r_t * g2pg1s);
+        const D1 v1 = dfms<NT>(gb, G1, kG1r_t * g2g1);
+        const D1 v3 = dfms<NT>(gb, pG1, kG1r_t * g2pg1);
+        const D1 v5 = dfms<NT>(gb, pg1s, kG1r_t * g2pg1s);
+        const D1 v2 = dfms<NT>(ph, G1, kG1dp_t * pG1);
+        const D1 v6 = dfms<NT>(ph, g2g1, kG1dp_t * g2pg1);
+        const D1 v4 = dfms<NT>(sb, pG1, kS2r_t * pg1s);
+        const D1 v7 = dfms<NT>(sb, g2pg1, kS2r_t * g2pg1s);
         const D1 sk = kSi_t * Sa;
-        stq(iSFK, dfma<1>(Dt_Si, lap(iSFK, Si), Si + sk));
-        stq(aSFK, dfma<1>(Dt_Sa, lap(aSFK, Sa), Sa - sk));
-        stq(GAB1, dfma<1>(Dt_G1, lap(GAB1, G1), G1 - v1 - v2));
-        stq(pGAB1, dfma<1>(Dt_G1, lap(pGAB1, pG1), pG1 - v3 + v2 - v4));
-        stq(GRB2, dfma<1>(Dt_G2, lap(GRB2, G2), G2 - v1 - v3 - v5));
-        stq(G2G1, dfma<1>(Dt_G2G1, lap(G2G1, g2g1), g2g1 + v1 - v6));
-        stq(G2PG1, dfma<1>(Dt_G2G1, lap(G2PG1, g2pg1), g2pg1 + v3 + v6 - v7));
-        stq(SHP2, dfma<1>(Dt_S2, lap(SHP2, S2), S2 - v4 - v7));
-        stq(PG1S, dfma<1>(Dt_G1S2, lap(PG1S, pg1s), pg1s + v4 - v5));
-        stq(G2PG1S, dfma<1>(Dt_G2G1S2, lap(G2PG1S, g2pg1s), g2pg1s + v5 + v7));
+        stq(iSFK, dfma<NT>(Dt_Si, lap(iSFK, Si), Si + sk));
+        stq(aSFK, dfma<NT>(Dt_Sa, lap(aSFK, Sa), Sa - sk));
+        stq(GAB1, dfma<NT>(Dt_G1, lap(GAB1, G1), G1 - v1 - v2));
+        stq(pGAB1, dfma<NT>(Dt_G1, lap(pGAB1, pG1), pG1 - v3 + v2 - v4));
+        stq(GRB2, dfma<NT>(Dt_G2, lap(GRB2, G2), G2 - v1 - v3 - v5));
+        stq(G2G1, dfma<NT>(Dt_G2G1, lap(G2G1, g2g1), g2g1 + v1 - v6));
+        stq(G2PG1, dfma<NT>(Dt_G2G1, lap(G2PG1, g2pg1), g2pg1 + v3 + v6 - v7));
+        stq(SHP2, dfma<NT>(Dt_S2, lap(SHP2, S2), S2 - v4 - v7));
+        stq(PG1S, dfma<NT>(Dt_G1S2, lap(PG1S, pg1s), pg1s + v4 - v5));
+        stq(G2PG1S, dfma<NT>(Dt_G2G1S2, lap(G2PG1S, g2pg1s), g2pg1s + v5 + v7));
       }
       if (mwarp) {
         // ---- membrane fixed point on duals (tangent_kernel.cuh); exit decided by the values ----
         const D1 m_old = x;
-        const D1 m_next = dshfl_down1<1>(m_old);
-        const D1 f = dfms<1>(m_old, dfma<1>(alpha2, m_old, alpha), beta * m_next);
-        const D1 fsrc = dshfl<1>(f, f_src);
+        const D1 m_next = dshfl_down1<NT>(m_old);
+        const D1 f = dfms<NT>(m_old, dfma<NT>(alpha2, m_old, alpha), beta * m_next);
+        const D1 fsrc = dshfl<NT>(f, f_src);
         D1 dm;
         dm.v = fma(s_own, f.v, s_src * fsrc.v);
-        dm.p[0] = fma(s_own, f.p[0], s_src * fsrc.p[0]);
-        const D1 base = dfma<1>(dt, dm, m_old);
-        const D1 Md1 = dshfl<1>(m_old, src_den), Mn1 = dshfl<1>(m_old, src_num);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) dm.p[n] = fma(s_own, f.p[n], s_src * fsrc.p[n]);
+        const D1 base = dfma<NT>(dt, dm, m_old);
+        const D1 Md1 = dshfl<NT>(m_old, src_den), Mn1 = dshfl<NT>(m_old, src_num);
         const D1 A_t = kf_t * Md1;
         const D1 B_t = kr_t * Mn1;
         __syncwarp();
-        D1 Iq = dconst<1>(0.0), Ii;
-        if (lane < NCY) { Iq.v = u_at(nxt, 0, lane, T - 2); Iq.p[0] = u_at(nxt, 1, lane, T - 2); }
-        Ii.v = u_at(nxt, 0, iSFK, T - 2); Ii.p[0] = u_at(nxt, 1, iSFK, T - 2);
-        const D1 cr = lane == aSFK ? dfma<1>(cf, Iq, ca * Ii) : cr_fixed;
+        D1 Iq = dconst<NT>(0.0), Ii;
+        if (lane < NCY) { Iq.v = u_at(nxt, 0, lane, T - 2);
+#pragma unroll
+          for (int n = 0; n < NT; ++n) Iq.p[n] = u_at(nxt, 1 + n, lane, T - 2); }
+        Ii.v = u_at(nxt, 0, iSFK, T - 2);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) Ii.p[n] = u_at(nxt, 1 + n, iSFK, T - 2);
+        const D1 cr = lane == aSFK ? dfma<NT>(cf, Iq, ca * Ii) : cr_fixed;
         int it = 0;
         D1 Mn = Mn1, Md = Md1;
         for (;;) {
           ++it;
-          const D1 num = dfma<1>(cr, Mn, Iq);
+          const D1 num = dfma<NT>(cr, Mn, Iq);
           D1 den = cf * Md;
           den.v += 1.0;
           const double rden = fast_recip(den.v);
           D1 qv;
           qv.v = num.v * rden;
-          qv.p[0] = fma(-qv.v, den.p[0], num.p[0]) * rden;
-          const D1 F = dfms<1>(A_t, qv, B_t);
-          const D1 F0 = dshfl<1>(F, fs0), F1 = dshfl<1>(F, fs1), F2 = dshfl<1>(F, fs2), F3 = dshfl<1>(F, fs3);
+#pragma unroll
+          for (int n = 0; n < NT; ++n) qv.p[n] = fma(-qv.v, den.p[n], num.p[n]) * rden;
+          const D1 F = dfms<NT>(A_t, qv, B_t);
+          const D1 F0 = dshfl<NT>(F, fs0), F1 = dshfl<NT>(F, fs1), F2 = dshfl<NT>(F, fs2), F3 = dshfl<NT>(F, fs3);
           D1 mnew;
           mnew.v = fma(sg0, F0.v, sg1 * F1.v) + fma(sg2, F2.v, fma(sg3, F3.v, base.v));
-          mnew.p[0] = fma(sg0, F0.p[0], sg1 * F1.p[0]) + fma(sg2, F2.p[0], fma(sg3, F3.p[0], base.p[0]));
+#pragma unroll
+          for (int n = 0; n < NT; ++n) mnew.p[n] = fma(sg0, F0.p[n], sg1 * F1.p[n]) + fma(sg2, F2.p[n], fma(sg3, F3.p[n], base.p[n]));
           const D1 xnew = lane < NCY ? qv : mnew;
           const bool ok = (fabs(x.v - xnew.v) < tol * fabs(x.v)) || untracked;
           x = xnew;
           if (__all_sync(FULL, ok)) break;
           if (it >= maxiters) break;
-          Mn = dshfl<1>(x, src_num);
-          Md = dshfl<1>(x, src_den);
+          Mn = dshfl<NT>(x, src_num);
+          Md = dshfl<NT>(x, src_den);
         }
         bc_total += it;
-        if (lane < NCY) { u_at(nxt, 0, lane, T - 1) = x.v; u_at(nxt, 1, lane, T - 1) = x.p[0]; }
+        if (lane < NCY) { u_at(nxt, 0, lane, T - 1) = x.v;
+#pragma unroll
+          for (int n = 0; n < NT; ++n) u_at(nxt, 1 + n, lane, T - 1) = x.p[n]; }
       }
       __syncthreads();
       cur = nxt;
@@ -316,12 +361,13 @@ team_tangent_kernel(const TangentArgs ta) {
           __syncthreads();
           if (a.o.out_mode == GAB1_OUT_FULL) write_column(col, cur);
           else if (col == Cn - 1) {
-            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
               __syncthreads();
               for (int n = tid; n < P; n += T) row[n] = stot_at(cur, c, n);
               __syncthreads();
               const double tr = trapz_r2(a.r, row, P);
-              if (c == 0) { pct_ave.v = tr; pct_memb.v = hdr[EG2PG1S]; } else { pct_ave.p[0] = tr; pct_memb.p[0] = hdr[16 + EG2PG1S]; }
+              if (c == 0) { pct_ave.v = tr; pct_memb.v = hdr[EG2PG1S]; } else { pct_ave.p[c > 0 ? c - 1 : 0] = tr; pct_memb.p[c > 0 ? c - 1 : 0] = hdr[16 * c + EG2PG1S]; }
             }
           }
           __syncthreads();
@@ -334,7 +380,7 @@ team_tangent_kernel(const TangentArgs ta) {
     const int fin = Nt == 0 ? 1 : cur;
     bool ns = false;
     if (a.o.out_mode == GAB1_OUT_FINAL4) {
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < NC; ++c) {
         if (!ob[c]) continue;
         for (int n = tid; n < P; n += T) {
           const double v0 = at_node(fin, c, iSFK, n), v1 = at_node(fin, c, aSFK, n), v2 = ptot_at(fin, c, n), v3 = stot_at(fin, c, n);
@@ -343,7 +389,7 @@ team_tangent_kernel(const TangentArgs ta) {
         }
       }
     } else if (a.o.out_mode == GAB1_OUT_FINAL_STATE) {
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < NC; ++c) {
         if (!ob[c]) continue;
         for (int q = 0; q < NCY; ++q)
           for (int n = tid; n < P; n += T) { const double v = at_node(fin, c, q, n); ob[c][(long long)q * P + n] = v; if (c == 0) ns |= isnan(v); }
@@ -356,14 +402,18 @@ team_tangent_kernel(const TangentArgs ta) {
       const double pct_v = (ave_v + mem_v) / CoG1.v * 100.0;
       ns |= isnan(pct_v);
       if (lead && tid == 0) oset[0] = pct_v;
-      const double ave_p = pct_ave.p[0] * 3.0 / R3, mem_p = pct_memb.p[0] * a.o.pct_mul / a.o.pct_div;
-      if (tid == 0) ob[1][0] = ((ave_p + mem_p) / CoG1.v - ((ave_v + mem_v) / CoG1.v) * (CoG1.p[0] / CoG1.v)) * 100.0;
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        if (!ob[1 + n]) continue;
+        const double ave_p = pct_ave.p[n] * 3.0 / R3, mem_p = pct_memb.p[n] * a.o.pct_mul / a.o.pct_div;
+        if (tid == 0) ob[1 + n][0] = ((ave_p + mem_p) / CoG1.v - ((ave_v + mem_v) / CoG1.v) * (CoG1.p[n] / CoG1.v)) * 100.0;
+      }
     }
     if (ns) status |= GAB1_ST_NAN;
     if (track_t && nts < Cn) {
       status |= GAB1_ST_SHORT;
       if (a.o.out_mode == GAB1_OUT_FULL) {
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < NC; ++c) {
           if (!ob[c]) continue;
           long long o2 = 0;
           for (int mi = 0; mi < 12; ++mi) {

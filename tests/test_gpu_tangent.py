@@ -282,13 +282,14 @@ def test_team_tangent_kernel(pkg, gfe, ofe, ensemble, mode, monkeypatch):
         if mode == "full":
             kw["matrices"] = ("aSFK", "PG1S", "G2PG1S", "PG1tot")
         ref = ofe.pdesolver_tangent_batch(Co, D, k, seeds, **kw)
-        for family in ("reg", "team"):
+        for family, nt in (("reg", ""), ("team", "1"), ("team", "2")):      # one or two directions per CTA (5 directions: ragged)
             monkeypatch.setenv("GAB1_TANGENT", family)
+            monkeypatch.setenv("GAB1_TANGENT_NT", nt)
             res = gfe.pdesolver_tangent_batch(Co, D, k, seeds, **kw)
             try:
                 check(res, ref, abi, (Co, D, k))
             except AssertionError as e:
-                raise AssertionError(f"{family} dr={dr}: {e}") from e
+                raise AssertionError(f"{family} nt={nt} dr={dr}: {e}") from e
 
 
 def test_fitting_gradient_full_length_final_stage_grid(pkg, gfe, ofe):
