@@ -319,7 +319,7 @@ int solve_tangent_device(const gab1_opts* o, int device, cudaStream_t stream, lo
     int nsm = 148;
     (void)cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
     int NTt = (n_dir >= 2 && o->Nr > 64 && S * (long long)n_dir > 8LL * nsm) ? 2 : 1;
-    if (const char* e = getenv("GAB1_TANGENT_NT")) { const int v = atoi(e); if (v == 1 || (v == 2 && n_dir >= 2)) NTt = v; }
+    if (const char* e = getenv("GAB1_TANGENT_NT")) { const int v = atoi(e); if (v == 1 || ((v == 2 || v == 4) && n_dir >= 2)) NTt = v; }
     ta.groups = (n_dir + NTt - 1) / NTt;
     return gab1::launch_team_tangent_kernel(NTt, ta, device, stream);
   }

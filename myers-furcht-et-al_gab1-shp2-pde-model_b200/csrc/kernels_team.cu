@@ -70,8 +70,9 @@ int launch_tt(const TangentArgs& ta, int device, cudaStream_t stream) {
 }
 }  // namespace
 
-// NT directions per CTA (1 or 2); ta.groups must be ceil(n_dir / NT)
+// NT directions per CTA (1, 2 or 4); ta.groups must be ceil(n_dir / NT)
 int launch_team_tangent_kernel(int NT, const TangentArgs& ta, int device, cudaStream_t stream) {
+  if (NT == 4) return launch_tt<4>(ta, device, stream);
   if (NT == 2) return launch_tt<2>(ta, device, stream);
   return launch_tt<1>(ta, device, stream);
 }

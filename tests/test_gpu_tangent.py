@@ -282,7 +282,7 @@ def test_team_tangent_kernel(pkg, gfe, ofe, ensemble, mode, monkeypatch):
         if mode == "full":
             kw["matrices"] = ("aSFK", "PG1S", "G2PG1S", "PG1tot")
         ref = ofe.pdesolver_tangent_batch(Co, D, k, seeds, **kw)
-        for family, nt in (("reg", ""), ("team", "1"), ("team", "2")):      # one or two directions per CTA (5 directions: ragged)
+        for family, nt in (("reg", ""), ("team", "1"), ("team", "2"), ("team", "4")):      # 1, 2 or 4 directions per CTA (5 directions: ragged)
             monkeypatch.setenv("GAB1_TANGENT", family)
             monkeypatch.setenv("GAB1_TANGENT_NT", nt)
             res = gfe.pdesolver_tangent_batch(Co, D, k, seeds, **kw)
