@@ -314,11 +314,12 @@ int solve_tangent_device(const gab1_opts* o, int device, cudaStream_t stream, lo
   CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp, bytes, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)S,
                                                      0, 32, stream));
   if (team) {
-    // directions per CTA: two share one primal (dr = 0.1, 1184 sets x 4 partials: 2.02 s against 2.62 s with one) once the batch
-    // fills the GPU; one per CTA is the latency optimum (one gradient: 127 vs 205 ms).  dr = 0.2: no difference at full size.
+    // directions per CTA: once the batch fills the GPU, up to four share one primal (coefficient partials in shared memory;
+    // dr = 0.1, 1184 sets x 4 partials: 1.77 s with four, 1.96 s with two, 2.62 s with one); one per CTA is the latency optimum
+    // (one gradient: 127 ms against 205 ms with two).  dr = 0.2: 1.18 / 1.24 s with two / four, the register kernel 1.19 s.
     int nsm = 148;
     (void)cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
-    int NTt = (n_dir >= 2 && o->Nr > 64 && S * (long long)n_dir > 8LL * nsm) ? 2 : 1;
+    int NTt = (n_dir >= 2 && o->Nr > 64 && S * (long long)n_dir > 8LL * nsm) ? (n_dir >= 3 ? 4 : 2) : 1;
     if (const char* e = getenv("GAB1_TANGENT_NT")) { const int v = atoi(e); if (v == 1 || ((v == 2 || v == 4) && n_dir >= 2)) NTt = v; }
     ta.groups = (n_dir + NTt - 1) / NTt;
     return gab1::launch_team_tangent_kernel(NTt, ta, device, stream);

@@ -44,7 +44,7 @@ int launch_tt(const TangentArgs& ta, int device, cudaStream_t stream) {
   const int T = 32 * W;
   if (T > 256) return fail(-6, "team tangent kernel: Nr = %d needs more than 8 warps", ta.a.o.Nr);
   constexpr int NC = 1 + NT;
-  const size_t smem = ((size_t)2 * NC * NCY * T + 16 * NC + (size_t)ta.a.P_pad) * sizeof(double);
+  const size_t smem = ((size_t)2 * NC * NCY * T + 16 * NC + (size_t)ta.a.P_pad + ((C_N * NT + 3) & ~3) + (size_t)L_N * NT * 32) * sizeof(double);
   auto kern = team_tangent_kernel<NT>;
   static std::mutex mu;
   static bool attr_set[64] = {false};

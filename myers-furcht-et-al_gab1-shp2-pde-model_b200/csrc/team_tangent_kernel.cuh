@@ -9,7 +9,7 @@
 // Measured: one gradient (4 partials) 127 ms at dr = 0.1, 33 ms at dr = 0.2 (one warp per pair: 577 and 60 ms).
 // Same restrictions as gab1_solve_tangent; arithmetic forms as tangent_kernel.cuh.
 #pragma once
-#include "tangent_kernel.cuh"
+#include "tangent_stream_kernel.cuh"     // the coefficient enums C_*, L_*
 
 namespace gab1 {
 
@@ -29,6 +29,11 @@ team_tangent_kernel(const TangentArgs ta) {
   double* U = smem;                                    // [2 buffers][NC components][NCY][T]
   double* hdr = smem + 2 * NC * NCY * T;               // [16 c, 16 c + 8): membrane values of component c
   double* row = hdr + 16 * NC;                         // P_pad doubles
+  // partials of the coefficients: C_N uniform ones (x NT), L_N + 2 per-lane ones of the membrane warp (x NT x 32) — in
+  // registers they spill as soon as a CTA carries more than one direction
+  const unsigned cps_s = (unsigned)__cvta_generic_to_shared(row + a.P_pad);
+  const unsigned lps_s = cps_s + 8u * (unsigned)(((C_N * NT + 3) & ~3));
+  auto ldc = [](unsigned addr) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v; };
   auto u_at = [&](int buf, int c, int q, int slot) -> double& { return U[((buf * NC + c) * NCY + q) * T + slot]; };
 
   const bool interior = node >= 1 && node <= Nr - 1;
@@ -153,34 +158,62 @@ team_tangent_kernel(const TangentArgs ta) {
     long long bc_total = 0;
     D1 pct_ave = dconst<NT>(0.0), pct_memb = dconst<NT>(0.0);
 
-    const D1 kS2f_t = kd(0) * dt, kS2r_t = kd(1) * dt, kG1f_t = kd(2) * dt, kG1r_t = kd(3) * dt, kG1p_t = kd(6) * dt,
-             kG1dp_t = kd(7) * dt, kSi_t = kd(9) * dt;
-    const D1 Dt_Si = D_Si * dt, Dt_Sa = D_Sa * dt, Dt_G1 = Dd(4) * dt, Dt_G2 = Dd(1) * dt, Dt_G2G1 = Dd(2) * dt,
-             Dt_S2 = Dd(6) * dt, Dt_G1S2 = Dd(5) * dt, Dt_G2G1S2 = Dd(3) * dt;
-
-    // ---- membrane block: lane roles of the last warp (tangent_kernel.cuh) ----
+    double cv[C_N];                 // values of the uniform coefficients; their partials: cps_s
+    double lv[L_N];                 // values of this lane's membrane coefficients (last warp); partials: lps_s
     constexpr int LZ = 31, LE = ML + NMB;
-    D1 kf = dconst<NT>(0.0), kr = dconst<NT>(0.0), Dq = dconst<NT>(1.0);
     int src_num = LZ, src_den = LZ;
-    switch (lane) {
-      case iSFK:   kf = kd(8); Dq = D_Si; src_den = LE; break;
-      case aSFK:   kf = kd(8); Dq = D_Si; src_num = LE; src_den = LE; break;
-      case GAB1:   kf = kd(2); kr = kd(3); Dq = Dd(4); src_num = ML + EG2G1;   src_den = ML + EG2;    break;
-      case pGAB1:  kf = kd(2); kr = kd(3); Dq = Dd(4); src_num = ML + EG2PG1;  src_den = ML + EG2;    break;
-      case GRB2:   kf = kd(4); kr = kd(5); Dq = Dd(1); src_num = ML + EG2;     src_den = ML + E;      break;
-      case G2G1:   kf = kd(4); kr = kd(5); Dq = Dd(2); src_num = ML + EG2G1;   src_den = ML + E;      break;
-      case G2PG1:  kf = kd(4); kr = kd(5); Dq = Dd(2); src_num = ML + EG2PG1;  src_den = ML + E;      break;
-      case SHP2:   kf = kd(0); kr = kd(1); Dq = Dd(6); src_num = ML + EG2PG1S; src_den = ML + EG2PG1; break;
-      case PG1S:   kf = kd(2); kr = kd(3); Dq = Dd(5); src_num = ML + EG2PG1S; src_den = ML + EG2;    break;
-      case G2PG1S: kf = kd(4); kr = kd(5); Dq = Dd(3); src_num = ML + EG2PG1S; src_den = ML + E;      break;
-      default: break;
+    {
+      auto put_c = [&](int c, const D1& v) { cv[c] = v.v;
+        if (tid == 0) {
+#pragma unroll
+          for (int n = 0; n < NT; ++n) sts(cps_s + 8u * (unsigned)(c * NT + n), v.p[n]);
+        } };
+      put_c(C_kS2f, kd(0) * dt); put_c(C_kS2r, kd(1) * dt); put_c(C_kG1f, kd(2) * dt); put_c(C_kG1r, kd(3) * dt);
+      put_c(C_kG1p, kd(6) * dt); put_c(C_kG1dp, kd(7) * dt); put_c(C_kSi, kd(9) * dt);
+      put_c(C_DSi, D_Si * dt); put_c(C_DSa, D_Sa * dt); put_c(C_DG1, Dd(4) * dt); put_c(C_DG2, Dd(1) * dt);
+      put_c(C_DG2G1, Dd(2) * dt); put_c(C_DS2, Dd(6) * dt); put_c(C_DG1S2, Dd(5) * dt); put_c(C_DG2G1S2, Dd(3) * dt);
+      put_c(C_dt, dt);
+      put_c(C_ca, kd(8) * drdiv<NT>(a.o.dr, D_Sa));
+      D1 kf = dconst<NT>(0.0), kr = dconst<NT>(0.0), Dq = dconst<NT>(1.0);
+      switch (lane) {
+        case iSFK:   kf = kd(8); Dq = D_Si; src_den = LE; break;
+        case aSFK:   kf = kd(8); Dq = D_Si; src_num = LE; src_den = LE; break;
+        case GAB1:   kf = kd(2); kr = kd(3); Dq = Dd(4); src_num = ML + EG2G1;   src_den = ML + EG2;    break;
+        case pGAB1:  kf = kd(2); kr = kd(3); Dq = Dd(4); src_num = ML + EG2PG1;  src_den = ML + EG2;    break;
+        case GRB2:   kf = kd(4); kr = kd(5); Dq = Dd(1); src_num = ML + EG2;     src_den = ML + E;      break;
+        case G2G1:   kf = kd(4); kr = kd(5); Dq = Dd(2); src_num = ML + EG2G1;   src_den = ML + E;      break;
+        case G2PG1:  kf = kd(4); kr = kd(5); Dq = Dd(2); src_num = ML + EG2PG1;  src_den = ML + E;      break;
+        case SHP2:   kf = kd(0); kr = kd(1); Dq = Dd(6); src_num = ML + EG2PG1S; src_den = ML + EG2PG1; break;
+        case PG1S:   kf = kd(2); kr = kd(3); Dq = Dd(5); src_num = ML + EG2PG1S; src_den = ML + EG2;    break;
+        case G2PG1S: kf = kd(4); kr = kd(5); Dq = Dd(3); src_num = ML + EG2PG1S; src_den = ML + E;      break;
+        default: break;
+      }
+      const D1 drD = drdiv<NT>(a.o.dr, Dq);
+      const bool is_flux = lane >= GAB1 && lane <= G2PG1S;
+      D1 alpha = dconst<NT>(0.0), alpha2 = dconst<NT>(0.0), beta = dconst<NT>(0.0);
+      switch (lane - ML) {
+        case mE:     alpha = kd(12) * kd(14); beta = kd(13); break;
+        case mES:    alpha2 = kd(15);         beta = kd(16); break;
+        case mESmES: alpha = kd(10);          beta = kd(11); break;
+        default: break;
+      }
+      auto put_l = [&](int c, const D1& v) { lv[c] = v.v;
+        if (mwarp) {
+#pragma unroll
+          for (int n = 0; n < NT; ++n) sts(lps_s + 8u * (unsigned)((c * NT + n) * 32 + lane), v.p[n]);
+        } };
+      put_l(L_cf, kf * drD);
+      put_l(L_cr, kr * drD);
+      put_l(L_kft, is_flux ? kf * dt : dconst<NT>(0.0));
+      put_l(L_krt, is_flux ? kr * dt : dconst<NT>(0.0));
+      put_l(L_alpha, alpha); put_l(L_alpha2, alpha2); put_l(L_beta, beta);
     }
-    const D1 drD = drdiv<NT>(a.o.dr, Dq);
-    const D1 cf = kf * drD;
-    const D1 cr_fixed = kr * drD;
-    const D1 ca = kd(8) * drdiv<NT>(a.o.dr, D_Sa);
-    const bool is_flux = lane >= GAB1 && lane <= G2PG1S;
-    const D1 kf_t = is_flux ? kf * dt : dconst<NT>(0.0), kr_t = is_flux ? kr * dt : dconst<NT>(0.0);
+    auto KC = [&](int c) { D1 r; r.v = cv[c];
+#pragma unroll
+      for (int n = 0; n < NT; ++n) r.p[n] = ldc(cps_s + 8u * (unsigned)(c * NT + n)); return r; };
+    auto LC = [&](int c) { D1 r; r.v = lv[c];
+#pragma unroll
+      for (int n = 0; n < NT; ++n) r.p[n] = ldc(lps_s + 8u * (unsigned)((c * NT + n) * 32 + lane)); return r; };
     int fs0 = LZ, fs1 = LZ, fs2 = LZ, fs3 = LZ;
     double sg0 = 0.0, sg1 = 0.0, sg2 = 0.0, sg3 = 0.0;
     switch (lane - ML) {
@@ -191,17 +224,17 @@ team_tangent_kernel(const TangentArgs ta) {
       case EG2PG1S: fs0 = G2PG1S; fs1 = PG1S;  fs2 = SHP2; sg0 = 1.0; sg1 = 1.0; sg2 = 1.0; break;
       default: break;
     }
-    D1 alpha = dconst<NT>(0.0), alpha2 = dconst<NT>(0.0), beta = dconst<NT>(0.0);
     double s_own = 0.0, s_src = 0.0;
     int f_src = LZ;
     switch (lane - ML) {
-      case mE:     alpha = kd(12) * kd(14); beta = kd(13); s_own = -1.0; break;
-      case mES:    alpha2 = kd(15);         beta = kd(16); s_own = -2.0; s_src = 1.0; f_src = ML + mE; break;
-      case mESmES: alpha = kd(10);          beta = kd(11); s_own = -1.0; s_src = 1.0; f_src = ML + mES; break;
+      case mE:     s_own = -1.0; break;
+      case mES:    s_own = -2.0; s_src = 1.0; f_src = ML + mE; break;
+      case mESmES: s_own = -1.0; s_src = 1.0; f_src = ML + mES; break;
       case E:      s_src = 1.0; f_src = ML + mESmES; break;
       case NMB:    s_src = 2.0; f_src = ML + mESmES; break;
       default: break;
     }
+    __syncthreads();                                     // coefficient partials visible
     const double tol = a.o.tol;
     const bool untracked = lane >= LE;
     const int maxiters = a.o.maxiters;
@@ -276,28 +309,31 @@ team_tangent_kernel(const TangentArgs ta) {
         auto stq = [&](int q, const D1& val) { u_at(nxt, 0, q, tid) = val.v;
 #pragma unroll
           for (int n = 0; n < NT; ++n) u_at(nxt, 1 + n, q, tid) = val.p[n]; };
-        const D1 gb = kG1f_t * G2, ph = kG1p_t * Sa, sb = kS2f_t * S2;
-        const D1 v1 = dfms<NT>(gb, G1, kG1r_t * g2g1);
-        const D1 v3 = dfms<NT>(gb, pG1, kG1r_t * g2pg1);
-        const D1 v5 = dfms<NT>(gb, pg1s, kG1r_t * g2pg1s);
-        const D1 v2 = dfms<NT>(ph, G1, kG1dp_t * pG1);
-        const D1 v6 = dfms<NT>(ph, g2g1, kG1dp_t * g2pg1);
-        const D1 v4 = dfms<NT>(sb, pG1, kS2r_t * pg1s);
-        const D1 v7 = dfms<NT>(sb, g2pg1, kS2r_t * g2pg1s);
-        const D1 sk = kSi_t * Sa;
-        stq(iSFK, dfma<NT>(Dt_Si, lap(iSFK, Si), Si + sk));
-        stq(aSFK, dfma<NT>(Dt_Sa, lap(aSFK, Sa), Sa - sk));
-        stq(GAB1, dfma<NT>(Dt_G1, lap(GAB1, G1), G1 - v1 - v2));
-        stq(pGAB1, dfma<NT>(Dt_G1, lap(pGAB1, pG1), pG1 - v3 + v2 - v4));
-        stq(GRB2, dfma<NT>(Dt_G2, lap(GRB2, G2), G2 - v1 - v3 - v5));
-        stq(G2G1, dfma<NT>(Dt_G2G1, lap(G2G1, g2g1), g2g1 + v1 - v6));
-        stq(G2PG1, dfma<NT>(Dt_G2G1, lap(G2PG1, g2pg1), g2pg1 + v3 + v6 - v7));
-        stq(SHP2, dfma<NT>(Dt_S2, lap(SHP2, S2), S2 - v4 - v7));
-        stq(PG1S, dfma<NT>(Dt_G1S2, lap(PG1S, pg1s), pg1s + v4 - v5));
-        stq(G2PG1S, dfma<NT>(Dt_G2G1S2, lap(G2PG1S, g2pg1s), g2pg1s + v5 + v7));
+        const D1 kg1r = KC(C_kG1r), kg1dp = KC(C_kG1dp), ks2r = KC(C_kS2r);
+        const D1 gb = KC(C_kG1f) * G2, ph = KC(C_kG1p) * Sa, sb = KC(C_kS2f) * S2;
+        const D1 v1 = dfms<NT>(gb, G1, kg1r * g2g1);
+        const D1 v3 = dfms<NT>(gb, pG1, kg1r * g2pg1);
+        const D1 v5 = dfms<NT>(gb, pg1s, kg1r * g2pg1s);
+        const D1 v2 = dfms<NT>(ph, G1, kg1dp * pG1);
+        const D1 v6 = dfms<NT>(ph, g2g1, kg1dp * g2pg1);
+        const D1 v4 = dfms<NT>(sb, pG1, ks2r * pg1s);
+        const D1 v7 = dfms<NT>(sb, g2pg1, ks2r * g2pg1s);
+        const D1 sk = KC(C_kSi) * Sa;
+        stq(iSFK, dfma<NT>(KC(C_DSi), lap(iSFK, Si), Si + sk));
+        stq(aSFK, dfma<NT>(KC(C_DSa), lap(aSFK, Sa), Sa - sk));
+        stq(GAB1, dfma<NT>(KC(C_DG1), lap(GAB1, G1), G1 - v1 - v2));
+        stq(pGAB1, dfma<NT>(KC(C_DG1), lap(pGAB1, pG1), pG1 - v3 + v2 - v4));
+        stq(GRB2, dfma<NT>(KC(C_DG2), lap(GRB2, G2), G2 - v1 - v3 - v5));
+        stq(G2G1, dfma<NT>(KC(C_DG2G1), lap(G2G1, g2g1), g2g1 + v1 - v6));
+        stq(G2PG1, dfma<NT>(KC(C_DG2G1), lap(G2PG1, g2pg1), g2pg1 + v3 + v6 - v7));
+        stq(SHP2, dfma<NT>(KC(C_DS2), lap(SHP2, S2), S2 - v4 - v7));
+        stq(PG1S, dfma<NT>(KC(C_DG1S2), lap(PG1S, pg1s), pg1s + v4 - v5));
+        stq(G2PG1S, dfma<NT>(KC(C_DG2G1S2), lap(G2PG1S, g2pg1s), g2pg1s + v5 + v7));
       }
       if (mwarp) {
         // ---- membrane fixed point on duals (tangent_kernel.cuh); exit decided by the values ----
+        const D1 cf = LC(L_cf), cr_fixed = LC(L_cr), kf_t = LC(L_kft), kr_t = LC(L_krt), alpha = LC(L_alpha), alpha2 = LC(L_alpha2),
+                 beta = LC(L_beta), dtd = KC(C_dt);
         const D1 m_old = x;
         const D1 m_next = dshfl_down1<NT>(m_old);
         const D1 f = dfms<NT>(m_old, dfma<NT>(alpha2, m_old, alpha), beta * m_next);
@@ -306,7 +342,7 @@ team_tangent_kernel(const TangentArgs ta) {
         dm.v = fma(s_own, f.v, s_src * fsrc.v);
 #pragma unroll
         for (int n = 0; n < NT; ++n) dm.p[n] = fma(s_own, f.p[n], s_src * fsrc.p[n]);
-        const D1 base = dfma<NT>(dt, dm, m_old);
+        const D1 base = dfma<NT>(dtd, dm, m_old);
         const D1 Md1 = dshfl<NT>(m_old, src_den), Mn1 = dshfl<NT>(m_old, src_num);
         const D1 A_t = kf_t * Md1;
         const D1 B_t = kr_t * Mn1;
@@ -318,7 +354,8 @@ team_tangent_kernel(const TangentArgs ta) {
         Ii.v = u_at(nxt, 0, iSFK, T - 2);
 #pragma unroll
         for (int n = 0; n < NT; ++n) Ii.p[n] = u_at(nxt, 1 + n, iSFK, T - 2);
-        const D1 cr = lane == aSFK ? dfma<NT>(cf, Iq, ca * Ii) : cr_fixed;
+        D1 cr = cr_fixed;
+        if (lane == aSFK) cr = dfma<NT>(cf, Iq, KC(C_ca) * Ii);
         int it = 0;
         D1 Mn = Mn1, Md = Md1;
         for (;;) {
@@ -352,7 +389,7 @@ team_tangent_kernel(const TangentArgs ta) {
       }
       __syncthreads();
       cur = nxt;
-      t = t + dt;
+      t = t + KC(C_dt);
       if (track_t && t.v >= t_save) {
         if (nts >= Cn) status |= GAB1_ST_OVERFLOW;
         else {
