@@ -101,7 +101,9 @@ def cpu_sample(pkg, nsets_per_thread=32):
     thread (about 20 CPU-seconds on 16 threads; enough sets per thread for the dynamic schedule to balance)."""
     from oracle import oracle
     o, Co, D, k, dt, r = workload(pkg)
-    threads = oracle.max_threads()
+    # every core this process may run on: torchrun exports OMP_NUM_THREADS=1 by default, which omp_get_max_threads() would
+    # follow and turn the N>1 reference arm into a one-thread run
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else oracle.max_threads()
     n = min(D.shape[0], nsets_per_thread * threads)
     be = oracle.OracleBackend(threads)
     t0 = time.perf_counter()
@@ -144,6 +146,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries the one JSON line: NCCL's version/debug banner (NCCL_DEBUG set on the box) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = pkg.abi.load_library()
     o, Co, D, k, dt, r = workload(pkg)
