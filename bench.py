@@ -146,9 +146,22 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries the one JSON line: NCCL's version/debug banner (NCCL_DEBUG set on the box) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # stdout carries the one JSON line: NCCL prints its version banner to stdout while the communicator is created
+        # (NCCL_DEBUG=VERSION on the box; NCCL_DEBUG_FILE is not honoured at that level), so fd 1 points at stderr meanwhile
+        libc = C.CDLL(None)
+        sys.stdout.flush()
+        libc.fflush(None)
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            libc.fflush(None)
+            os.dup2(saved, 1)
+            os.close(saved)
     lib = pkg.abi.load_library()
     o, Co, D, k, dt, r = workload(pkg)
     S = D.shape[0]
