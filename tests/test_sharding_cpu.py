@@ -82,3 +82,29 @@ def test_two_ranks_gloo_shards_gather_to_single_rank_result(pkg):
     np.testing.assert_array_equal(gathered, ref.out)
     assert tmax == pytest.approx(0.2)
     assert bounds[0] == 0 and bounds[2] == 12 and bounds[1] < 6     # the heavy set pulls the boundary left
+
+
+def _ref_arm(env_extra, sets=None):
+    import json
+    import subprocess
+    env = dict(os.environ, **env_extra)
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                         env=env, capture_output=True, text=True, timeout=300, check=True).stdout
+    return out, json
+
+
+def test_reference_arm_under_torchrun_env():
+    """bench.py --impl reference as the driver launches it for N > 1: rank 0 prints exactly one JSON line and uses every core of
+    its affinity mask although torchrun exports OMP_NUM_THREADS=1; the other ranks print nothing and exit 0."""
+    import __graft_entry__ as g
+    g.build()
+    out, json = _ref_arm({"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0", "OMP_NUM_THREADS": "1"})
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["metric"] == "ensemble PDE solves/sec"
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["value"] > 0
+    out, _ = _ref_arm({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1", "OMP_NUM_THREADS": "1"})
+    assert out.strip() == ""
