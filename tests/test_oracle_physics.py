@@ -87,3 +87,29 @@ def test_oracle_kat(pkg, ofe, ensemble):
     res = ofe.pdesolver_batch(Co, sub[:, :7], sub[:, 7:], dr=0.25, tf=0.5, Nts=5, tol=1e-4, maxiters=20,
                               geometry=pkg.abi.GEOM_RECT, pg1tot_form=pkg.abi.PG1TOT_CHAIN)
     np.testing.assert_array_equal(res.out, kat["full_rect_dr025_tf05"])
+
+
+def test_stored_mle_is_a_constrained_optimum_of_the_oracle_loss(pkg, ofe):
+    """A pin on an artefact the reference itself computed: fitted_parameters.csv is the result of its bound-constrained
+    LBFGS fit of `loss` (param_fitting+inference_finitediff.jl:188-226,254-270; final stage dr = 0.1, tol = 1e-3, box =
+    prior mode x 10^+-2, :177-183).  Three of the four constants are stored AT a box bound (kG1p = 100 x 0.42, kG1dp =
+    kSi = 9.5 / 100) and kSa in the interior.  Under the oracle's loss and forward-mode gradient the stored point must
+    satisfy the optimality conditions of that problem: the gradient pushes every bounded constant outwards through its
+    active bound, the free one is stationary (orders of magnitude below the others), and the loss is below the loss at
+    the optimiser's starting point p0 and at the posterior medians."""
+    P = pkg.params
+    mu, sigma = 26.426, 9.363293460636593                      # exptl_pct_SHP2-bound-GAB1.csv
+    names = ("kG1p", "kG1dp", "kSa", "kSi")
+    mle = np.array([P.FITTED_MLE[n] for n in names])
+    p0 = np.array([0.42, 9.5, 0.42, 9.5])                        # prior modes (SURVEY §8d: exp(-0.86750), exp(2.25129))
+    assert np.allclose(mle[[0, 1, 3]], [p0[0] * 100, p0[1] / 100, p0[3] / 100], rtol=1e-12)
+    assert p0[2] / 100 < mle[2] < p0[2] * 100
+    pv = np.concatenate([P.DIFFS_BASE, P.KVALS_BASE])
+    x = np.log(np.stack([mle, p0, P.KVALS_BASE[6:10]]))
+    loss, grad, yhat = ofe.fitting_loss_and_gradient(x, mu, sigma, param_inds=[13, 14, 15, 16], pvals0=pv, Co=P.base_Co(),
+                                                    dr=0.1, tol=1e-3, maxiters=20)
+    assert loss[0] < loss[1] and loss[0] < loss[2]
+    assert loss[0] < 2.0e-3 and abs(yhat[0] - 26.03) < 0.05    # the plateau below the data mean: yhat cannot reach 26.43
+    g = grad[0]
+    assert g[0] < 0 and g[1] > 0 and g[3] > 0                    # upper bound active; lower bounds active
+    assert abs(g[2]) < 1e-2 * min(abs(g[0]), abs(g[1]))          # free parameter: stationary
