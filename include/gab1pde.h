@@ -188,9 +188,15 @@ int gab1_solve_batch_device(const gab1_opts* o, int32_t device, void* stream, in
                             int64_t* n_steps, int64_t* n_bc_iters,
                             void* workspace);
 
-/* The sharding gab1_solve_batch applies: bounds[g]..bounds[g+1] is the contiguous range of set indices device g
- * solves; ranges are balanced by total step count ceil(tf/dt).  Pure host code; bounds has n_shards+1 entries. */
+/* The sharding gab1_solve_batch applies (no collective: the parameter sets are independent, get_param_posteriors.jl:147,
+ * sapdesolver.jl:377).  Pure host code; bounds has n_shards+1 entries.
+ *   gab1_plan_shards  full snapshot output: bounds[g]..bounds[g+1] is the contiguous range of set indices device g solves,
+ *                     balanced by total step count ceil(tf/dt), so that a device's result is one block of `out`;
+ *   gab1_deal_shards  small per-set outputs (FINAL4 / SIX / PCT_BOUND / FINAL_STATE): the sets in descending step-count
+ *                     order go one by one to the least-loaded shard (LPT) — equal total work AND the same mix of long, short and
+ *                     diverging solves per device; perm[bounds[g] .. bounds[g+1]) are shard g's set indices (ascending). */
 int gab1_plan_shards(int64_t S, const double* dt, double tf, int32_t n_shards, int64_t* bounds);
+int gab1_deal_shards(int64_t S, const double* dt, double tf, int32_t n_shards, int64_t* perm, int64_t* bounds);
 
 /*
  * Order statistics across the parameter sets of an ensemble — what the reference's figure scripts compute from the stacked
@@ -279,6 +285,11 @@ void gab1_release_device_memory(void);
  * snapshots straight into it while the time loop runs (no device copy of the output, no D2H phase). */
 void* gab1_host_alloc(size_t bytes);
 void gab1_host_free(void* p);
+/* Same, with the pages placed on the NUMA node the GPU `device` is attached to (the calling thread is moved onto that
+ * node's CPUs while the pages are touched); falls back to gab1_host_alloc where the platform exposes no topology.
+ * gab1_device_numa_node: that node, or -1.  GAB1_NUMA=0 in the environment disables the placement. */
+void* gab1_host_alloc_near(size_t bytes, int32_t device);
+int gab1_device_numa_node(int32_t device);
 
 /* Sustained FP64 FMA rate of `device` in TFLOP/s (2 flop per DFMA), measured by a register-resident
  * DFMA kernel; the roofline denominator bench.py reports. Negative on failure. */

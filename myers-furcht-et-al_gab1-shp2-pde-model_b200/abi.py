@@ -115,8 +115,9 @@ def _ptr(a, typ):
     return None if a is None else a.ctypes.data_as(typ)
 
 
-def call_solve(fn, o: Opts, Co, D, k, dt, r, *extra):
-    """Marshal numpy arrays into a gab1_solve_batch-shaped function and return its outputs."""
+def call_solve(fn, o: Opts, Co, D, k, dt, r, *extra, alloc_out=None):
+    """Marshal numpy arrays into a gab1_solve_batch-shaped function and return its outputs.
+    alloc_out(n_doubles) -> flat float64 array supplies the output block (default: zero-filled pageable memory)."""
     D = np.ascontiguousarray(D, dtype=np.float64).reshape(-1, N_D)
     k = np.ascontiguousarray(k, dtype=np.float64).reshape(-1, N_K)
     S = D.shape[0]
@@ -137,7 +138,7 @@ def call_solve(fn, o: Opts, Co, D, k, dt, r, *extra):
         # the reference indexes r[Nr+1] (basepdesolver.jl:151,206); a shorter grid is a BoundsError there
         raise IndexError(f"r has {r.shape[0]} nodes but Nr+1 = {o.Nr + 1}")
     n = out_doubles_per_set(o)
-    out = np.zeros((S, n), dtype=np.float64)
+    out = np.zeros((S, n), dtype=np.float64) if alloc_out is None else alloc_out(S * n).reshape(S, n)
     status = np.zeros(S, dtype=np.int32)
     n_saved = np.zeros(S, dtype=np.int32)
     n_steps = np.zeros(S, dtype=np.int64)
@@ -222,8 +223,14 @@ def load_library():
     lib.gab1_default_dt.restype = C.c_int
     lib.gab1_plan_shards.argtypes = [C.c_int64, _dp, C.c_double, C.c_int32, _i64p]
     lib.gab1_plan_shards.restype = C.c_int
+    lib.gab1_deal_shards.argtypes = [C.c_int64, _dp, C.c_double, C.c_int32, _i64p, _i64p]
+    lib.gab1_deal_shards.restype = C.c_int
     lib.gab1_host_alloc.argtypes = [C.c_size_t]
     lib.gab1_host_alloc.restype = C.c_void_p
+    lib.gab1_host_alloc_near.argtypes = [C.c_size_t, C.c_int32]
+    lib.gab1_host_alloc_near.restype = C.c_void_p
+    lib.gab1_device_numa_node.argtypes = [C.c_int32]
+    lib.gab1_device_numa_node.restype = C.c_int
     lib.gab1_host_free.argtypes = [C.c_void_p]
     lib.gab1_host_free.restype = None
     lib.gab1_release_device_memory.argtypes = []
@@ -270,15 +277,29 @@ class CudaBackend:
 
     name = "cuda"
 
-    def __init__(self, n_devices: int = 1, arith: int = ARITH_FAST):
-        self.n_devices = n_devices
+    # output blocks of at least this many bytes come from the pinned pool: the kernels then write the caller's buffer
+    # directly while the time loop runs (gab1pde.h, gab1_host_alloc) instead of a staged copy into pageable memory
+    PINNED_FROM_BYTES = 32 << 20
+
+    def __init__(self, n_devices: int = 1, arith: int = ARITH_FAST, device_ids=None):
+        self.n_devices = n_devices if device_ids is None else len(device_ids)
         self.arith = arith
+        self.device_ids = None if device_ids is None else (C.c_int32 * len(device_ids))(*device_ids)
+
+    def _bind(self, o: Opts):
+        o.n_devices = self.n_devices
+        o.device_ids = None if self.device_ids is None else C.cast(self.device_ids, C.POINTER(C.c_int32))
+
+    def _alloc_out(self, n: int):
+        if n * 8 >= self.PINNED_FROM_BYTES:
+            return pinned_pool_array(n, np.float64, device=self.device_ids[0] if self.device_ids is not None else 0)
+        return np.empty(n, dtype=np.float64)           # the kernels write every element of every set's block
 
     def solve(self, o: Opts, Co, D, k, dt, r):
         lib = load_library()
-        o.n_devices = self.n_devices
+        self._bind(o)
         o.arith = self.arith
-        rc, out, status, n_saved, n_steps, n_bc = call_solve(lib.gab1_solve_batch, o, Co, D, k, dt, r)
+        rc, out, status, n_saved, n_steps, n_bc = call_solve(lib.gab1_solve_batch, o, Co, D, k, dt, r, alloc_out=self._alloc_out)
         if rc != 0:
             raise Gab1Error(f"gab1_solve_batch failed ({rc}): {lib.gab1_last_error().decode(errors='replace')}")
         return out, status, n_saved, n_steps, n_bc
@@ -286,7 +307,7 @@ class CudaBackend:
     def solve_tangent(self, o: Opts, Co, D, k, dt, seeds, r):
         """Values and forward-mode partials along the seed directions (gab1_solve_tangent)."""
         lib = load_library()
-        o.n_devices = self.n_devices
+        self._bind(o)
         rc, out, status, n_saved, n_steps, n_bc = call_solve_tangent(lib.gab1_solve_tangent, o, Co, D, k, dt, seeds, r)
         if rc != 0:
             raise Gab1Error(f"gab1_solve_tangent failed ({rc}): {lib.gab1_last_error().decode(errors='replace')}")
@@ -299,6 +320,7 @@ class CudaBackend:
     def solve_quantiles(self, o: Opts, Co, D, k, dt, r, matrices: int, c0: int, c1: int, probs):
         """Solve on one GPU, keep the FULL result in HBM, return order statistics across the sets (gab1pde.h)."""
         lib = load_library()
+        self._bind(o)
         o.n_devices = 1
         o.arith = self.arith
         D = np.ascontiguousarray(D, dtype=np.float64).reshape(-1, N_D)
@@ -365,6 +387,73 @@ def plan_shards(dt, tf: float, n_shards: int) -> np.ndarray:
     if lib.gab1_plan_shards(dt.shape[0], _ptr(dt, _dp), float(tf), n_shards, _ptr(bounds, _i64p)) != 0:
         raise Gab1Error(lib.gab1_last_error().decode())
     return bounds
+
+
+def deal_shards(dt, tf: float, n_shards: int):
+    """(perm, bounds): perm[bounds[g]:bounds[g+1]] are the set indices device/rank g solves when the sets are dealt from
+    the descending step-count order (gab1_deal_shards: the plan for small per-set outputs)."""
+    lib = load_library()
+    dt = np.ascontiguousarray(dt, dtype=np.float64)
+    perm = np.zeros(dt.shape[0], dtype=np.int64)
+    bounds = np.zeros(n_shards + 1, dtype=np.int64)
+    if lib.gab1_deal_shards(dt.shape[0], _ptr(dt, _dp), float(tf), n_shards, _ptr(perm, _i64p), _ptr(bounds, _i64p)) != 0:
+        raise Gab1Error(lib.gab1_last_error().decode())
+    return perm, bounds
+
+
+class _PinnedPool:
+    """Pinned, device-mapped host blocks kept between calls: pinning 2.5 GB costs ~0.5 s, re-using a block nothing.
+    A block returns here when the array that wraps it (and every view of it) has been garbage-collected."""
+
+    def __init__(self, keep_bytes: int = 8 << 30):
+        self.keep_bytes = keep_bytes
+        self.free = {}          # (nbytes, device) -> [pointer]
+        self.held = 0
+
+    def take(self, nbytes: int, device: int):
+        lst = self.free.get((nbytes, device))
+        if lst:
+            self.held -= nbytes
+            return lst.pop()
+        lib = load_library()
+        p = lib.gab1_host_alloc_near(nbytes, device)
+        if not p:
+            self.trim(0)
+            p = lib.gab1_host_alloc_near(nbytes, device)
+        if not p:
+            raise MemoryError(lib.gab1_last_error().decode())
+        return p
+
+    def give(self, p, nbytes: int, device: int):
+        if self.held + nbytes > self.keep_bytes:
+            load_library().gab1_host_free(p)
+            return
+        self.free.setdefault((nbytes, device), []).append(p)
+        self.held += nbytes
+
+    def trim(self, keep_bytes: int):
+        lib = load_library()
+        for key, lst in list(self.free.items()):
+            while lst and self.held > keep_bytes:
+                lib.gab1_host_free(lst.pop())
+                self.held -= key[0]
+
+
+_POOL = _PinnedPool()
+
+
+def pinned_pool_array(n: int, dtype=np.float64, device: int = 0) -> np.ndarray:
+    """A flat array of pinned, device-mapped host memory near `device` that goes back to the pool when it is collected."""
+    import weakref
+    nbytes = max(int(n) * np.dtype(dtype).itemsize, 8)
+    p = _POOL.take(nbytes, device)
+    base = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,))
+    weakref.finalize(base, _POOL.give, p, nbytes, device)
+    return base.view(dtype)[:n]
+
+
+def release_pinned_pool() -> None:
+    _POOL.trim(0)
 
 
 def pinned_empty(n: int, dtype=np.float64):

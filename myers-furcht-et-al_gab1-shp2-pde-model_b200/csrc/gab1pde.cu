@@ -1,7 +1,9 @@
 // gab1pde.cu — C ABI of libgab1pde.so (include/gab1pde.h): option checking, work ordering, kernel launch,
 // multi-GPU sharding of the host entry point.  No CPU implementation of the solver lives here.
 #include <cuda_runtime.h>
+#include <ctype.h>
 #include <math.h>
+#include <sched.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -428,7 +430,39 @@ struct DeviceArena {
   size_t cap = 0;
 };
 static DeviceArena g_arena[64];
+// per-set outputs up to this many doubles are sharded by dealing (gather / scatter on the host), larger ones contiguously
+static const int64_t kDealtMaxDoubles = 8192;
 static size_t& arena_prev_cap(int device) { static size_t prev[64] = {0}; return prev[device]; }
+
+
+// Grow a device's arena to at least `need` bytes.  cudaFree + cudaMalloc cost 20-500 ms on a 180 GB device (measured), so
+// the arena starts at 64 MB and grows by at least half / doubles while it is small — but never asks for more than the
+// device can give: the request is capped by the free memory (after the old slab is released) and falls back to the exact
+// size, so a shard that fits the budget never fails on the growth margin.
+static int arena_reserve(DeviceArena& ar, int device, size_t need) {
+  if (need <= ar.cap) return 0;
+  if (ar.base) { CUDA_TRY(cudaStreamSynchronize(ar.stream)); cudaFree(ar.base); ar.base = nullptr; ar.cap = 0; }
+  size_t want = need + need / 2;
+  if (want < ((size_t)64 << 20)) want = (size_t)64 << 20;
+  if (want < 2 * arena_prev_cap(device) && arena_prev_cap(device) <= ((size_t)4 << 30)) want = 2 * arena_prev_cap(device);
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+    const size_t room = free_b > ((size_t)256 << 20) ? free_b - ((size_t)256 << 20) : free_b;
+    if (want > room) want = room;
+  } else {
+    (void)cudaGetLastError();
+  }
+  if (want < need) want = need;
+  if (cudaMalloc((void**)&ar.base, want) != cudaSuccess) {
+    (void)cudaGetLastError();
+    ar.base = nullptr;
+    want = need;
+    CUDA_TRY(cudaMalloc((void**)&ar.base, want));
+  }
+  ar.cap = want;
+  arena_prev_cap(device) = want;
+  return 0;
+}
 
 // gab1_solve_ensemble_quantiles: the FULL result stays on the device and only order statistics come back
 struct QReq {
@@ -443,7 +477,10 @@ static size_t device_budget_bytes(int device) {
   if (const char* e = getenv("GAB1_MAX_DEVICE_BYTES")) { const long long v = atoll(e); if (v > 0) return (size_t)v; }
   size_t free_b = 0, total_b = 0;
   if (cudaSetDevice(device) != cudaSuccess || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
-  return total_b / 100 * 85;
+  const size_t by_total = total_b / 100 * 85, by_free = free_b > ((size_t)1 << 30) ? free_b - ((size_t)1 << 30) : free_b / 2;
+  size_t held = 0;       // this library's own slab on the device is reusable
+  if (device >= 0 && device < 64) held = g_arena[device].cap;
+  return by_total < by_free + held ? by_total : by_free + held;
 }
 
 // One shard of the host entry point: copy in, solve, copy out, on its device's stream.
@@ -507,17 +544,7 @@ static int run_shard(const gab1_opts* o, int device, int64_t lo, int64_t hi, con
   const bool dbg = getenv("GAB1_DEBUG_TIMING") != nullptr;
   auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
   const double t_a = now();
-  if (off > ar.cap) {
-    if (ar.base) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(ar.base); ar.base = nullptr; ar.cap = 0; }
-    // cudaFree + cudaMalloc cost 20-500 ms on a 180 GB device (measured): start at 64 MB and at least double, so that a
-    // session of calls with growing batches re-allocates a handful of times at most
-    size_t want = off + off / 2;
-    if (want < ((size_t)64 << 20)) want = (size_t)64 << 20;
-    if (want < 2 * arena_prev_cap(device) && arena_prev_cap(device) <= ((size_t)4 << 30)) want = 2 * arena_prev_cap(device);
-    CUDA_TRY(cudaMalloc((void**)&ar.base, want));
-    ar.cap = want;
-    arena_prev_cap(device) = want;
-  }
+  if (int e = arena_reserve(ar, device, off)) return e;
   const double t_b = now();
   if (dbg) fprintf(stderr, "[gab1] run_shard S=%lld arena %.1f ms (cap %zu)\n", (long long)S, 1e3 * (t_b - t_a), ar.cap);
   double *dCo = (double*)(ar.base + oCo), *dD = (double*)(ar.base + oD), *dk = (double*)(ar.base + oK),
@@ -593,11 +620,20 @@ static int run_tangent_shard(const gab1_opts* o, int device, int64_t lo, int64_t
   if (S <= 0) return 0;
   if (device < 0 || device >= 64) return fail(-7, "device ordinal %d out of range", device);
   CUDA_TRY(cudaSetDevice(device));
+  const int64_t nout = gab1_out_doubles_per_set(o) * (1 + n_dir);
+  if (S > 1) {      // a shard whose staged output and seeds would not fit the device is solved in pieces (as run_shard does)
+    const size_t budget = device_budget_bytes(device);
+    const size_t per_set = (size_t)nout * sizeof(double) + (size_t)n_dir * GAB1_N_SEED * sizeof(double) + 512;
+    if (budget && (size_t)S * per_set > budget) {
+      const int64_t mid = lo + S / 2;
+      if (int e = run_tangent_shard(o, device, lo, mid, n_dir, Co, Co_stride, D, k, dt, seeds, r, out, status, n_saved, n_steps, n_bc)) return e;
+      return run_tangent_shard(o, device, mid, hi, n_dir, Co, Co_stride, D, k, dt, seeds, r, out, status, n_saved, n_steps, n_bc);
+    }
+  }
   DeviceArena& ar = g_arena[device];
   std::lock_guard<std::mutex> lk(ar.mu);
   if (!ar.stream) CUDA_TRY(cudaStreamCreateWithFlags(&ar.stream, cudaStreamNonBlocking));
   cudaStream_t st = ar.stream;
-  const int64_t nout = gab1_out_doubles_per_set(o) * (1 + n_dir);
   const size_t P = (size_t)o->Nr + 1;
   const size_t nCo = Co_stride ? (size_t)S * GAB1_N_CO : GAB1_N_CO;
   const size_t nSeed = (size_t)S * n_dir * GAB1_N_SEED;
@@ -609,15 +645,7 @@ static int run_tangent_shard(const gab1_opts* o, int device, int64_t lo, int64_t
                oSv = take((size_t)S * sizeof(int32_t)), oNs = take((size_t)S * sizeof(int64_t)),
                oBc = take((size_t)S * sizeof(int64_t)), oWs = take(gab1_workspace_bytes(S)),
                oOut = take((size_t)S * nout * sizeof(double));
-  if (off > ar.cap) {
-    if (ar.base) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(ar.base); ar.base = nullptr; ar.cap = 0; }
-    size_t want = off + off / 2;
-    if (want < ((size_t)64 << 20)) want = (size_t)64 << 20;
-    if (want < 2 * arena_prev_cap(device) && arena_prev_cap(device) <= ((size_t)4 << 30)) want = 2 * arena_prev_cap(device);
-    CUDA_TRY(cudaMalloc((void**)&ar.base, want));
-    ar.cap = want;
-    arena_prev_cap(device) = want;
-  }
+  if (int e = arena_reserve(ar, device, off)) return e;
   double *dCo = (double*)(ar.base + oCo), *dD = (double*)(ar.base + oD), *dk = (double*)(ar.base + oK),
          *ddt = (double*)(ar.base + oDt), *dsd = (double*)(ar.base + oSd), *dr_ = (double*)(ar.base + oR),
          *dout = (double*)(ar.base + oOut);
@@ -759,22 +787,95 @@ int gab1_solve_batch(const gab1_opts* o, int64_t S, const double* Co, int64_t Co
   std::vector<int> devs(nd);
   for (int i = 0; i < nd; ++i) devs[i] = o->device_ids ? o->device_ids[i] : i;
 
-  std::vector<int64_t> bounds(nd + 1, 0);
-  gab1_plan_shards(S, dt, o->tf, nd, bounds.data());
   if (nd == 1) return run_shard(o, devs[0], 0, S, Co, Co_stride, D, k, dt, r, out, status, n_saved, n_steps, n_bc_iters);
 
+  std::vector<int64_t> bounds(nd + 1, 0);
   std::vector<int> rcs(nd, 0);
   std::vector<std::string> msgs(nd);
   std::vector<std::thread> th;
-  for (int g = 0; g < nd; ++g)
-    th.emplace_back([&, g]() {
-      rcs[g] = run_shard(o, devs[g], bounds[g], bounds[g + 1], Co, Co_stride, D, k, dt, r, out, status, n_saved, n_steps,
-                         n_bc_iters);
-      if (rcs[g]) msgs[g] = g_err;
-    });
+  const int64_t nout = gab1_out_doubles_per_set(o);
+  const char* plan_env = getenv("GAB1_SHARD_PLAN");       // contiguous | dealt (A/B measurements, tests)
+  const bool dealt = plan_env && plan_env[0] ? strcmp(plan_env, "dealt") == 0 : nout <= kDealtMaxDoubles;
+  if (dealt) {
+    // Small per-set outputs (final profiles, six scalars, one percentage): the sets are dealt to the devices from the
+    // descending step-count order, so that every device receives the same mix of long and short solves (and of the
+    // diverging ones, which are cheap) whatever the order of the caller's matrix; each device's sets are gathered into
+    // contiguous staging rows, solved as one local batch, and scattered back to their columns.
+    std::vector<int64_t> perm((size_t)S);
+    gab1_deal_shards(S, dt, o->tf, nd, perm.data(), bounds.data());
+    for (int g = 0; g < nd; ++g)
+      th.emplace_back([&, g]() {
+        const int64_t lo = bounds[g], n = bounds[g + 1] - lo;
+        if (n <= 0) return;
+        const int64_t* idx = perm.data() + lo;
+        std::vector<double> lD((size_t)n * GAB1_N_D), lk((size_t)n * GAB1_N_K), ldt((size_t)n), lCo(Co_stride ? (size_t)n * GAB1_N_CO : 0),
+            lout((size_t)n * nout);
+        std::vector<int32_t> lst((size_t)n), lsv((size_t)n);
+        std::vector<int64_t> lns((size_t)n), lbc((size_t)n);
+        for (int64_t i = 0; i < n; ++i) {
+          const int64_t j = idx[i];
+          memcpy(&lD[(size_t)i * GAB1_N_D], D + j * GAB1_N_D, GAB1_N_D * sizeof(double));
+          memcpy(&lk[(size_t)i * GAB1_N_K], k + j * GAB1_N_K, GAB1_N_K * sizeof(double));
+          ldt[(size_t)i] = dt[j];
+          if (Co_stride) memcpy(&lCo[(size_t)i * GAB1_N_CO], Co + j * Co_stride, GAB1_N_CO * sizeof(double));
+        }
+        rcs[g] = run_shard(o, devs[g], 0, n, Co_stride ? lCo.data() : Co, Co_stride, lD.data(), lk.data(), ldt.data(), r,
+                           lout.data(), lst.data(), lsv.data(), lns.data(), lbc.data());
+        if (rcs[g]) { msgs[g] = g_err; return; }
+        for (int64_t i = 0; i < n; ++i) {
+          const int64_t j = idx[i];
+          memcpy(out + j * nout, &lout[(size_t)i * nout], (size_t)nout * sizeof(double));
+          if (status) status[j] = lst[(size_t)i];
+          if (n_saved) n_saved[j] = lsv[(size_t)i];
+          if (n_steps) n_steps[j] = lns[(size_t)i];
+          if (n_bc_iters) n_bc_iters[j] = lbc[(size_t)i];
+        }
+      });
+  } else {
+    // Full snapshot output (0.5 MB per set and more): contiguous ranges balanced by step count, so that each device's
+    // result lands in the caller's buffer as one block (or is written there by the kernels, when the buffer is mapped).
+    gab1_plan_shards(S, dt, o->tf, nd, bounds.data());
+    for (int g = 0; g < nd; ++g)
+      th.emplace_back([&, g]() {
+        rcs[g] = run_shard(o, devs[g], bounds[g], bounds[g + 1], Co, Co_stride, D, k, dt, r, out, status, n_saved, n_steps,
+                           n_bc_iters);
+        if (rcs[g]) msgs[g] = g_err;
+      });
+  }
   for (auto& t : th) t.join();
   for (int g = 0; g < nd; ++g)
     if (rcs[g]) return fail(rcs[g], "device %d: %s", devs[g], msgs[g].c_str());
+  return 0;
+}
+
+// Dealt shards: the sets in descending step-count order go, one by one, to the shard with the least work so far (LPT),
+// which keeps the shards' total step counts within one short solve of each other AND gives every shard the same
+// distribution of solve lengths; perm[bounds[g] .. bounds[g+1]) lists shard g's set indices in ascending order.
+int gab1_deal_shards(int64_t S, const double* dt, double tf, int32_t n_shards, int64_t* perm, int64_t* bounds) {
+  if (S < 0 || n_shards < 1 || !dt || !perm || !bounds) return fail(-2, "bad arguments to gab1_deal_shards");
+  std::vector<std::pair<double, int64_t>> w((size_t)S);
+  for (int64_t i = 0; i < S; ++i) {
+    const double n = ceil(tf / dt[i]);
+    w[(size_t)i] = {(n > 0.0 && n < 4.0e9) ? n : 1.0, i};
+  }
+  std::stable_sort(w.begin(), w.end(), [](const std::pair<double, int64_t>& a, const std::pair<double, int64_t>& b) { return a.first > b.first; });
+  std::vector<int32_t> shard_of((size_t)S);
+  std::vector<int64_t> count((size_t)n_shards, 0);
+  std::vector<double> load((size_t)n_shards, 0.0);
+  for (int64_t p = 0; p < S; ++p) {
+    // longest-processing-time rule: the next-longest solve goes to the least-loaded shard (ties: the fewest sets, then
+    // the lowest ordinal); with thousands of sets per shard the totals end within one short solve of each other
+    int32_t g = 0;
+    for (int32_t c = 1; c < n_shards; ++c)
+      if (load[(size_t)c] < load[(size_t)g] || (load[(size_t)c] == load[(size_t)g] && count[(size_t)c] < count[(size_t)g])) g = c;
+    shard_of[(size_t)w[(size_t)p].second] = g;
+    load[(size_t)g] += w[(size_t)p].first;
+    ++count[(size_t)g];
+  }
+  bounds[0] = 0;
+  for (int g = 0; g < n_shards; ++g) bounds[g + 1] = bounds[g] + count[(size_t)g];
+  std::vector<int64_t> fill(bounds, bounds + n_shards);
+  for (int64_t i = 0; i < S; ++i) perm[fill[(size_t)shard_of[(size_t)i]]++] = i;
   return 0;
 }
 
@@ -807,6 +908,67 @@ void* gab1_host_alloc(size_t bytes) {
     return nullptr;
   }
   return p;
+}
+
+// The NUMA node a GPU hangs off and that node's CPUs (sysfs); false when the platform does not say.
+static bool cpus_near_device(int device, cpu_set_t* set, int* node_out) {
+  char bus[32] = "";
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  char path[256];
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return false;
+  int node = -1;
+  const int got = fscanf(f, "%d", &node);
+  fclose(f);
+  if (got != 1 || node < 0) return false;
+  snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+  f = fopen(path, "r");
+  if (!f) return false;
+  char list[4096] = "";
+  const bool ok = fgets(list, sizeof list, f) != nullptr;
+  fclose(f);
+  if (!ok) return false;
+  CPU_ZERO(set);
+  int n = 0;
+  for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    int a = 0, b = 0;
+    const int k = sscanf(tok, "%d-%d", &a, &b);
+    if (k == 1) b = a;
+    if (k < 1) continue;
+    for (int c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET(c, set); ++n; }
+  }
+  if (node_out) *node_out = node;
+  return n > 0;
+}
+
+// Pinned, mapped host memory whose pages live on the NUMA node of `device`: the calling thread is moved onto that node's
+// CPUs while the pages are allocated and touched (Linux allocates on the toucher's node), then put back.  On a two-socket
+// 8-GPU box every GPU then streams its snapshots into its own socket's DRAM instead of across the inter-socket link.
+void* gab1_host_alloc_near(size_t bytes, int32_t device) {
+  cpu_set_t old_set, near_set;
+  const char* e = getenv("GAB1_NUMA");
+  const bool want = !(e && e[0] == '0');
+  bool moved = false;
+  if (want && sched_getaffinity(0, sizeof old_set, &old_set) == 0 && cpus_near_device(device, &near_set, nullptr)) {
+    cpu_set_t both;
+    CPU_AND(&both, &old_set, &near_set);
+    if (CPU_COUNT(&both) > 0) moved = sched_setaffinity(0, sizeof both, &both) == 0;
+  }
+  void* p = gab1_host_alloc(bytes);
+  if (p && moved) {
+    volatile char* c = (volatile char*)p;
+    for (size_t i = 0; i < bytes; i += 4096) c[i] = 0;
+  }
+  if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
+  return p;
+}
+
+int gab1_device_numa_node(int32_t device) {
+  cpu_set_t set;
+  int node = -1;
+  return cpus_near_device(device, &set, &node) ? node : -1;
 }
 void gab1_host_free(void* p) {
   if (p) cudaFreeHost(p);

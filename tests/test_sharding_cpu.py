@@ -32,6 +32,35 @@ def test_plan_is_contiguous_balanced_and_complete(pkg, ensemble):
     assert b[0] == 0 and b[-1] == 4 and np.all(np.diff(b) >= 0)
 
 
+def test_dealt_plan_is_a_balanced_partition_with_the_same_mix_everywhere(pkg):
+    """gab1_deal_shards (the plan for small per-set outputs, and the one bench.py's ranks use): a partition of the set
+    indices, ascending inside a shard, equal total step counts, and the same distribution of solve lengths per shard."""
+    import __graft_entry__ as g
+    g.build()
+    ens = pkg.params.synthetic_prior_ensemble(20000, seed=7)
+    dt = pkg.params.default_dt(ens[:, :7], ens[:, 7:], 0.2)
+    nt = np.ceil(5.0 / dt)
+    for n in (1, 2, 3, 8):
+        perm, b = pkg.abi.deal_shards(dt, 5.0, n)
+        assert sorted(perm.tolist()) == list(range(len(dt)))
+        assert b[0] == 0 and b[-1] == len(dt) and np.diff(b).max() - np.diff(b).min() <= max(2, len(dt) // (50 * n))
+        loads, q90 = [], []
+        for i in range(n):
+            idx = perm[b[i]:b[i + 1]]
+            assert np.all(np.diff(idx) > 0)
+            loads.append(nt[idx].sum())
+            q90.append(np.quantile(nt[idx], 0.9))
+        assert max(loads) / np.mean(loads) < 1.0005
+        assert max(q90) / min(q90) < 1.01
+    # fewer sets than shards, empty input, unusable dt
+    perm, b = pkg.abi.deal_shards(np.array([1e-3, 2e-3]), 1.0, 4)
+    assert sorted(perm.tolist()) == [0, 1] and b[-1] == 2 and np.diff(b).max() == 1
+    perm, b = pkg.abi.deal_shards(np.zeros(0), 1.0, 2)
+    assert list(b) == [0, 0, 0]
+    perm, b = pkg.abi.deal_shards(np.array([np.nan, 0.0, 1e-3, 1e-3]), 1.0, 2)
+    assert sorted(perm.tolist()) == [0, 1, 2, 3]
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, str(ROOT))
     import importlib
