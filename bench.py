@@ -271,7 +271,7 @@ def run_ours(args):
     # for the lower one (`frac` uses the lower)
     n_steps = res["n_steps"].astype(np.float64)
     n_bc = res["n_bc"].astype(np.float64)
-    nan = (res["status"] & abi.ST_NAN) != 0
+    nan = (res["status"] & (abi.ST_NAN | abi.ST_THROW)) != 0     # diverged: NaN reached the outputs / the reduction threw
     per_set = n_steps * (o.Nr - 1) * F_INT_SPH + n_bc * F_BC
     flops_all, flops_live = float(per_set.sum()), float(per_set[~nan].sum())
     kernel_ms = float(np.mean(res["ms"]))
@@ -383,7 +383,7 @@ def run_ours(args):
     ms1 = allmax(sum(res1["ms"]))
     value1 = world * S1 * args.steps / (ms1 * 1e-3)
     per1 = res1["n_steps"].astype(np.float64) * (o1.Nr - 1) * F_INT_SPH + res1["n_bc"].astype(np.float64) * F_BC
-    nan1 = (res1["status"] & abi.ST_NAN) != 0
+    nan1 = (res1["status"] & (abi.ST_NAN | abi.ST_THROW)) != 0
     ach1 = float(per1[~nan1].sum()) / (float(np.mean(res1["ms"])) * 1e-3) / 1e12
     kw1 = dict(dr=CFG1["dr"], tf=CFG1["tf"], Nts=CFG1["Nts"], tol=CFG1["tol"], maxiters=CFG1["maxiters"])
     r0 = fe.pdesolver_batch(Co1, D1, k1, **kw1)           # warm-up: pins the 2.5 GB output block once (kept in the pool)

@@ -5,7 +5,7 @@
  * The reference (pauljmyers/Myers-Furcht-et-al_GAB1-SHP2-PDE-model) has no FFI layer:
  * its boundary is the Julia call surface.  Each entry point below names the Julia
  * function(s) it stands in for (file:line under the reference's Julia/ directory).
- * A Julia maintainer binds these with `ccall` (see INTEGRATION.md and julia/GAB1PDE.jl).
+ * A Julia maintainer binds these with `ccall` (see INTEGRATION.md and julia/gab1pde_dropin.jl).
  *
  * All buffers are owned by the caller.  Plain pointers and sizes only.
  * Every function returns 0 on success and a negative code on failure; the message

@@ -2,7 +2,7 @@
 
 Every function keeps the name, argument meaning, keyword defaults and return shape of the Julia function
 it mirrors (file:line cited per function; all under the reference's Julia/ directory), so that the parity
-tests read like the reference's own call sites.  The Julia twin of this file is julia/GAB1PDE.jl.
+tests read like the reference's own call sites.  The Julia twin of this file is julia/gab1pde_dropin.jl.
 
 `Frontend(backend)` binds the surface to a backend object with a `.solve(opts, Co, D, k, dt, r)` method.
 The module-level functions are bound to the CUDA library (abi.CudaBackend); tests bind a second Frontend
@@ -102,7 +102,7 @@ class Frontend:
         return self._run(o, Co, Dmat, kmat, dt, dr, _grid(R, dr, r))
 
     def sapdesolver_batch(self, Co, Dmat, kmat, *, R=10.0, dr=0.2, tf=5.0, dt=None, maxiters=20, tol=1e-3,
-                          membSFK=False, out_mode=abi.OUT_FINAL4, r=None, iter_cap=100_000) -> BatchResult:
+                          membSFK=False, out_mode=abi.OUT_FINAL4, r=None, iter_cap=2000) -> BatchResult:
         """Batched sibling of sapdesolver / sapdesolver_membSFK (sapdesolver.jl:55-280, sapdesolver_memb-SFK.jl:55-281)."""
         o = abi.make_opts(R=R, dr=dr, tf=tf, Nts=1, maxiters=maxiters, tol=tol, out_mode=out_mode,
                           sfk_mode=abi.SFK_MEMBRANE if membSFK else abi.SFK_DIFFUSIBLE,
@@ -111,8 +111,10 @@ class Frontend:
         if membSFK:
             # `maxiters` is accepted but unused by the while-loop form (sapdesolver_memb-SFK.jl:58,177): a fixed point
             # that never meets `tol` spins forever in the reference.  The library needs a finite cap to stay bounded
-            # and reports GAB1_ST_ITER_CAP for a set that reaches it (2.6 % of wide synthetic ensembles do; convergent
-            # steps take 1-50 passes)
+            # and reports GAB1_ST_ITER_CAP for a set that reaches it.  The default comes from a sweep over caps
+            # (tools/cap_sweep.py, profiles/r2_cap_sweep_*.jsonl): on 20 000 HeLa sets (posterior-like and wide-prior) the
+            # SAME sets are flagged at every cap from 20 to 100 000 — a step that converges at all does so in fewer than
+            # 20 passes — and the pass time is flat up to ~5000; 2000 leaves a 100x margin (2.5-2.7 % of the sets reach it)
             o.maxiters = int(iter_cap)
         return self._run(o, Co, Dmat, kmat, dt, dr, _grid(R, dr, r))
 
@@ -163,8 +165,11 @@ class Frontend:
         res = self.pdesolver_batch(Co, np.asarray(D, float)[None, :], np.asarray(k, float)[None, :], **kw, **fixed)
         if res.status[0] & abi.ST_THROW:
             raise ArithmeticError("InexactError: Int64(ceil(tf/dt))")      # basepdesolver.jl:72
-        if res.status[0] & abi.ST_OVERFLOW and not trim:
-            raise IndexError("BoundsError: more than Nts+1 snapshots are due")   # basepdesolver.jl:271
+        if res.status[0] & abi.ST_OVERFLOW:
+            # basepdesolver.jl:271 raises BoundsError; the rect solvers grow their outputs instead
+            # (basepdesolver_rect.jl:250-279) — the library's block holds Nts+1 columns, so it refuses rather than truncates
+            raise IndexError("more than Nts+1 snapshots are due (BoundsError in pdesolver; beyond the library's fixed-size "
+                             "output for the rect solvers)")
         ncol = int(res.n_saved[0]) if trim else res.opts.Nts + 1
         mats = [res.matrix(n)[0][:, :ncol] for n in abi.MATRIX_NAMES]
         vecs = [res.vector(n)[0][:ncol] for n in abi.VECTOR_NAMES]
@@ -336,6 +341,7 @@ class Frontend:
         rect = name == "pdesolver_rect"
         mats = {n: res.matrix(n) for n in abi.MATRIX_NAMES}
         vecs = {n: res.vector(n) for n in abi.VECTOR_NAMES}
+        self._raise_like_the_reference(res)
         rows = []
         for j in range(ensemble.shape[0]):
             if res.status[j] & abi.ST_NAN:
@@ -347,6 +353,19 @@ class Frontend:
             rows.append(EnsembleRow(res.r, v[10], sol, j + 1))      # 1-based index as in Julia
         return rows
 
+    @staticmethod
+    def _raise_like_the_reference(res):
+        """The reference's threaded loops let a solver exception out (get_param_posteriors.jl:147-163): an InexactError from
+        Int64(ceil(tf/dt)), a BoundsError from a snapshot beyond column Nts+1.  (pdesolver_rect grows its outputs without
+        bound instead, basepdesolver_rect.jl:250-279; the library's output block holds Nts+1 columns, so more snapshots
+        than that is an error here rather than a silent truncation.)"""
+        bad = np.flatnonzero(res.status & abi.ST_THROW)
+        if len(bad):
+            raise ArithmeticError(f"InexactError: Int64(ceil(tf/dt)) for set {int(bad[0]) + 1} (and {len(bad) - 1} more)")
+        bad = np.flatnonzero(res.status & abi.ST_OVERFLOW)
+        if len(bad):
+            raise IndexError(f"more than Nts+1 snapshots are due for set {int(bad[0]) + 1} (and {len(bad) - 1} more)")
+
     def run_ensemble_pc(self, model_fun, ensemble, Co, *, dr=0.2, R=10.0, t_prechase=5.0, t_chase=2.0, Nts=100,
                         tol=1e-4, maxit=20, D_inds=range(0, 7), k_inds=range(7, 24)):
         """run_ensemble_pc (get_param_posteriors.jl:204-236) over pulsechase_solver."""
@@ -355,6 +374,7 @@ class Frontend:
                                    tf=t_prechase + t_chase, Nts=Nts, tol=tol, maxiters=maxit, t_prechase=t_prechase)
         mats = {n: res.matrix(n) for n in abi.MATRIX_NAMES}
         vecs = {n: res.vector(n) for n in abi.VECTOR_NAMES}
+        self._raise_like_the_reference(res)
         rows = []
         for j in range(ensemble.shape[0]):
             if res.status[j] & abi.ST_NAN:
