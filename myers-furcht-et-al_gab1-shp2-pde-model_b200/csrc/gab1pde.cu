@@ -92,6 +92,30 @@ FastPick pick_fast(int Nr) {
   return {32, fit(32), 0};
 }
 
+// Shape of the several-sets-per-warp kernels for a grid: G lanes per set, KN node slots per lane, Nr <= G*KN; the
+// narrowest gang that holds the grid (most sets per warp), then the shortest run.  GAB1_GANG="G,KN" overrides (A/B).
+struct GangPick { int G, KN; };
+GangPick pick_gang(int Nr) {
+  if (const char* e = getenv("GAB1_GANG")) {
+    int G = 0, KN = 0;
+    if (sscanf(e, "%d,%d", &G, &KN) == 2 && G * KN >= Nr) return {G, KN};
+  }
+  static const GangPick table[] = {{2, 7}, {2, 13}, {4, 7}, {4, 10}, {4, 13}, {8, 7}, {8, 13}, {16, 13}, {32, 8}, {32, 13}};
+  for (const GangPick& g : table)
+    if (Nr <= g.G * g.KN) return g;
+  return {0, 0};
+}
+int launch_gang(int G, int KN, int mode, const gab1::KernelArgs& a, int device, cudaStream_t stream) {
+  switch (G) {
+    case 2: return gab1::launch_gang_kernel_g2(KN, mode, a, device, stream);
+    case 4: return gab1::launch_gang_kernel_g4(KN, mode, a, device, stream);
+    case 8: return gab1::launch_gang_kernel_g8(KN, mode, a, device, stream);
+    case 16: return gab1::launch_gang_kernel_g16(KN, mode, a, device, stream);
+    case 32: return gab1::launch_gang_kernel_g32(KN, mode, a, device, stream);
+  }
+  return fail(-6, "no gang kernel for G = %d", G);
+}
+
 // ---- descending-work ordering: key = number of time steps, largest first -------------------------------------
 // Thread 0 also sets the guard word the pair kernels check: their spherical stencil drops the zero-flux mirror term of
 // node 1, which is exact only when 1 - dr/r[1] == 0, i.e. on the reference's own grid r = collect(0:dr:R).  For any
@@ -136,6 +160,25 @@ size_t carve(Workspace& w, void* base, long long S) {
   return off;
 }
 
+// The several-sets-per-warp kernel, then the one-set-per-warp kernel over the sets the first one handed back (those
+// that hit the iteration limit step after step: in a gang they would stall their warp's other sets).  Both launches are
+// enqueued back to back; the second reads its queue length from device memory, so there is no host synchronisation.
+int solve_with_gangs(const GangPick& gp, int mode, gab1::KernelArgs a, const Workspace& w, int device, cudaStream_t stream) {
+  const bool retry = !getenv("GAB1_GANG_NO_RETRY");
+  if (retry) { a.retry_count = w.counter + 2; a.retry_list = w.vals_in; }      // vals_in is free once the sort has run
+  if (int rc = launch_gang(gp.G, gp.KN, mode, a, device, stream)) return rc;
+  if (!retry) return 0;
+  gab1::KernelArgs b = a;
+  b.retry_count = nullptr; b.retry_list = nullptr;
+  b.order = w.vals_in;
+  b.counter = w.counter + 3;
+  b.dyn_count = w.counter + 2;
+  b.guard = nullptr;
+  const int K = pick_K(a.o.Nr);
+  return K ? gab1::launch_single_kernel(K, mode, b, device, stream)
+           : gab1::launch_stream_kernel(16, mode, b, device, stream);
+}
+
 int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long S, const double* Co, long long Co_stride,
                  const double* D, const double* k, const double* dt, const double* r, double* out, int* status,
                  int* n_saved, long long* n_steps, long long* n_bc, void* workspace) {
@@ -164,7 +207,7 @@ int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long 
   a.R_pow3 = pow(o->R, 3.0);
   a.P_pad = (o->Nr + 1 + 3) & ~3;
 
-  CUDA_TRY(cudaMemsetAsync(w.counter, 0, sizeof(unsigned), stream));
+  CUDA_TRY(cudaMemsetAsync(w.counter, 0, 4 * sizeof(unsigned), stream));
   {
     const int tb = 256;
     work_keys_kernel<<<(unsigned)((S + tb - 1) / tb), tb, 0, stream>>>(S, dt, o->tf, w.keys_in, w.vals_in, r, o->dr,
@@ -203,6 +246,19 @@ int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long 
     if (const char* m = getenv("GAB1_TEAM_MAX_SETS")) { if (m[0]) max_sets = atoll(m); }
     if ((named && strcmp(e, "team") == 0) || (!named && S <= max_sets))
       return gab1::launch_team_kernel(mode, a, device, stream);
+  }
+  // ---- large grids: several sets per warp, the state in shared memory (gang_kernel.cuh).  Measured on B200, full batches
+  //      (DESIGN.md section 5): Nr = 200 310 ms against 348 ms streamed; Nr = 400 1123 ms against 2036 ms; at Nr <= 128
+  //      the register-resident kernels below still win (Nr = 50: 393-467 ms against 424 ms; Nr = 25: 93 against 45 ms).
+  //      GAB1_KERNEL=gang forces the family on any grid, GAB1_GANG="G,KN" the shape (A/B measurements, parity tests).
+  if (mode != gab1::MODE_STRICT) {
+    const char* e = getenv("GAB1_KERNEL");
+    const bool named = e && e[0];
+    if ((named && strcmp(e, "gang") == 0) || (!named && o->Nr > 128)) {
+      const GangPick gp = pick_gang(o->Nr);
+      if (!gp.G) return fail(-6, "Nr = %d: no gang kernel holds this grid", o->Nr);
+      return solve_with_gangs(gp, mode, a, w, device, stream);
+    }
   }
   if (mode != gab1::MODE_STRICT) {
     const char* e = getenv("GAB1_KERNEL");
@@ -306,7 +362,7 @@ int solve_tangent_device(const gab1_opts* o, int device, cudaStream_t stream, lo
     if (const char* e = getenv("GAB1_TANGENT")) { if (strcmp(e, "team") == 0) team = true; else if (e[0]) team = false; }
   }
   ta.groups = (n_dir + NT - 1) / NT;
-  CUDA_TRY(cudaMemsetAsync(w.counter, 0, sizeof(unsigned), stream));
+  CUDA_TRY(cudaMemsetAsync(w.counter, 0, 4 * sizeof(unsigned), stream));
   const int tb = 256;
   work_keys_kernel<<<(unsigned)((S + tb - 1) / tb), tb, 0, stream>>>(S, dt, o->tf, w.keys_in, w.vals_in, r, o->dr, 0,
                                                                      (int*)(w.counter + 1));

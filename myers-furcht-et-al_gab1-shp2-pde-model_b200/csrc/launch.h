@@ -20,6 +20,12 @@ struct KernelArgs {
   int P_pad;                 // doubles per staged row in shared memory
   const int* guard;          // when non-null the kernel runs only if *guard == guard_expect (see gab1pde.cu)
   int guard_expect;
+  // hand-over between kernel families (gang_kernel.cuh): a several-sets-per-warp kernel appends the sets it gives up on
+  // (every step runs into the iteration limit) to retry_list; the one-set-per-warp kernel enqueued behind it solves
+  // exactly those, its queue ending at *dyn_count
+  unsigned int* retry_count;
+  int* retry_list;
+  const unsigned int* dyn_count;
 };
 
 enum { MODE_FAST_FOR = 0, MODE_FAST_WHILE = 1, MODE_STRICT = 2 };
@@ -46,6 +52,12 @@ int launch_group32_kernel(int K, int variant, int mode, bool mirror, const Kerne
 int launch_stream_kernel(int K, int mode, const KernelArgs& args, int device, cudaStream_t stream);
 // latency kernel (team_kernel.cuh): one CTA of ceil(Nr/32) warps per set, 32 < Nr <= 256, fast modes only
 int launch_team_kernel(int mode, const KernelArgs& args, int device, cudaStream_t stream);
+// several sets per warp (gang_kernel.cuh): G lanes per set (one translation unit per G), KN node slots per lane
+int launch_gang_kernel_g2(int KN, int mode, const KernelArgs& args, int device, cudaStream_t stream);
+int launch_gang_kernel_g4(int KN, int mode, const KernelArgs& args, int device, cudaStream_t stream);
+int launch_gang_kernel_g8(int KN, int mode, const KernelArgs& args, int device, cudaStream_t stream);
+int launch_gang_kernel_g16(int KN, int mode, const KernelArgs& args, int device, cudaStream_t stream);
+int launch_gang_kernel_g32(int KN, int mode, const KernelArgs& args, int device, cudaStream_t stream);
 // order statistics across the sets of a FULL result (ensemble_stats.cu); all pointers but `p` are device pointers
 size_t quantiles_workspace_bytes(long long S);
 int ensemble_quantiles_device(const gab1_opts* o, int device, cudaStream_t stream, long long S, const double* out,

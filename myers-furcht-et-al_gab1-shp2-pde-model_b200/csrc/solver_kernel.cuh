@@ -944,7 +944,7 @@ solve_kernel(const KernelArgs a) {
     unsigned item = 0;
     if (lane == 0) item = atomicAdd(a.counter, 1u);
     item = __shfl_sync(FULL, item, 0);
-    if ((long long)item >= a.S) break;
+    if ((long long)item >= a.S || (a.dyn_count && item >= *a.dyn_count)) break;
     const long long set = a.order ? (long long)a.order[item] : (long long)item;
     solve_set<K, MODE>(a, set, lane, ws, g);
     __syncwarp();

@@ -22,7 +22,7 @@ team_kernel(const KernelArgs a) {
   constexpr bool WHILE = MODE == MODE_FAST_WHILE;
   extern __shared__ double smem[];
   __shared__ unsigned s_item;
-  __shared__ int s_dead;
+  __shared__ int s_dead[2];      // indexed by the parity of the step: a warp that runs ahead raises the OTHER slot
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x, W = T >> 5;
   const bool mwarp = warp == W - 1;                    // the warp that owns nodes Nr-31..Nr and runs the membrane block
   const int Nr = a.o.Nr, P = Nr + 1, Nts = a.o.Nts, Cn = Nts + 1;
@@ -49,7 +49,7 @@ team_kernel(const KernelArgs a) {
 
   for (;;) {
     __syncthreads();
-    if (tid == 0) { s_item = atomicAdd(a.counter, 1u); s_dead = 0; }
+    if (tid == 0) { s_item = atomicAdd(a.counter, 1u); s_dead[0] = 0; s_dead[1] = 0; }
     __syncthreads();
     const unsigned item = s_item;
     if ((long long)item >= a.S) break;
@@ -316,11 +316,15 @@ team_kernel(const KernelArgs a) {
         bc_total += it;
         if (lane < NCY) u_at(nxt, lane, T - 1) = x;            // the boundary node Nr
         flag_check = unconverged || nan_exit;
-        if (flag_check && lane == 0) s_dead = 1;                  // ask the team to test for an all-NaN state
+        if (flag_check && lane == 0) s_dead[step & 1] = 1;        // ask the team to test for an all-NaN state
       }
       __syncthreads();                                            // the new time level is complete
       cur = nxt;
-      if (s_dead) {                                               // uniform: written before the barrier
+      // every warp has passed this step's barrier, so nobody reads the previous step's slot any more: the membrane warp
+      // clears it here, before it can raise it again at the next step (the slots alternate, so a membrane warp that is
+      // a whole step ahead of a slow warp never touches the flag that warp is about to read)
+      if (mwarp && lane == 0) s_dead[(step & 1) ^ 1] = 0;
+      if (s_dead[step & 1]) {                                     // uniform: written before the barrier
         const bool mine = !(node >= 1 && node <= Nr) ||
                           (isnan(u_at(cur, iSFK, tid)) && isnan(u_at(cur, aSFK, tid)) && isnan(u_at(cur, GAB1, tid)) &&
                            isnan(u_at(cur, pGAB1, tid)) && isnan(u_at(cur, GRB2, tid)) && isnan(u_at(cur, G2G1, tid)) &&
@@ -328,7 +332,6 @@ team_kernel(const KernelArgs a) {
                            isnan(u_at(cur, G2PG1S, tid)));
         const bool memb = !mwarp || (lane < ML || lane >= LE) || isnan(x);
         dead = __syncthreads_and(mine && memb);
-        if (mwarp && lane == 0) s_dead = 0;                       // the thread that raises the flag also clears it
         if (dead) countdown = 1;
       }
       t = t + dt;

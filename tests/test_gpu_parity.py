@@ -296,6 +296,9 @@ FAMILIES = {
     "stream": [0.2, 0.1, 0.05, 0.025],
     # latency path: one CTA of 2 / 4 / 7 warps per set (team_kernel.cuh)
     "team": [0.25, 0.2, 0.1, 0.05],
+    # several sets per warp, G lanes per set, the state in shared memory (gang_kernel.cuh): the default for Nr > 128;
+    # G = 2 / 4 / 4 / 8 / 16 / 32 on these grids
+    "gang": [0.4, 0.25, 0.2, 0.1, 0.05, 0.025],
 }
 
 
@@ -379,7 +382,7 @@ def test_output_larger_than_the_device_budget_is_solved_in_pieces(pkg, gfe, ense
     check_control_flow(pieces, whole)
 
 
-@pytest.mark.parametrize("family", ["", "legacy", "group16", "group32", "stream", "team"])
+@pytest.mark.parametrize("family", ["", "legacy", "group16", "group32", "stream", "team", "gang"])
 def test_runs_are_bitwise_repeatable(pkg, gfe, ensemble, family, monkeypatch):
     """compute-sanitizer is not available on this pool; a data race between lanes or warps (exchange headers, staged rows, the
     work queue) would show up as run-to-run differences.  2500 sets (more than two waves, every warp of a CTA busy, the dynamic
@@ -398,7 +401,7 @@ def test_runs_are_bitwise_repeatable(pkg, gfe, ensemble, family, monkeypatch):
         check_control_flow(a, b)
 
 
-@pytest.mark.parametrize("family", ["legacy", "group16", "group32", "stream", "team"])
+@pytest.mark.parametrize("family", ["legacy", "group16", "group32", "stream", "team", "gang"])
 def test_blow_up_takes_the_dead_state_path_in_every_family(pkg, gfe, ofe, ensemble, family, monkeypatch):
     """A time step 2.5x the stability limit blows every set up within a few hundred steps: values overflow, turn NaN, and the
     kernels' all-NaN fast-forward (clock and snapshot schedule only) takes over.  Status words, step counts, snapshot counts
@@ -407,7 +410,7 @@ def test_blow_up_takes_the_dead_state_path_in_every_family(pkg, gfe, ofe, ensemb
     Co = pkg.params.base_Co()
     rows = [0, 1, 2, 3, 4999]
     D, k = ensemble[rows, :7], ensemble[rows, 7:]
-    for dr in {"legacy": (0.2, 0.1), "group16": (0.4, 0.2), "group32": (0.2, 0.05), "stream": (0.2, 0.05, 0.025), "team": (0.1, 0.05)}[family]:
+    for dr in {"legacy": (0.2, 0.1), "group16": (0.4, 0.2), "group32": (0.2, 0.05), "stream": (0.2, 0.05, 0.025), "team": (0.1, 0.05), "gang": (0.2, 0.05, 0.025)}[family]:
         dt = 2.5 * pkg.params.default_dt(D, k, dr)
         kw = dict(dr=dr, tf=3000 * float(dt.max()), Nts=6, dt=dt, tol=1e-4, maxiters=20)
         res = gfe.pdesolver_batch(Co, D, k, **kw)
