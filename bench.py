@@ -278,6 +278,18 @@ def run_ours(args):
     achieved = flops_live / (kernel_ms * 1e-3) / 1e12
     achieved_all = flops_all / (kernel_ms * 1e-3) / 1e12
 
+    # The critical path of a batch is its longest member: one parameter set is a serial chain of Nt steps on one warp.
+    # Each rank times its longest set alone; the maximum over ranks is a lower bound of ms_per_step at ANY number of GPUs.
+    nt_all = np.ceil(CFG["tf"] / dt)
+    j = int(np.argmax(nt_all[mine]))
+    one = resident(o, Co, Dm[j:j + 1], km[j:j + 1], dtm[j:j + 1], r, 1, 1)
+    longest_alone_ms = allmax(one["ms"][0])
+    limits = {"longest_solve_steps": int(nt_all.max()), "median_solve_steps": int(np.median(nt_all)),
+              "longest_solve_alone_ms": longest_alone_ms,
+              "note": "a parameter set is one serial chain of steps on one warp: no split of the ensemble over more GPUs can "
+                      "finish before its longest member does (heavy-tailed priors: the time step shrinks with the sum of the "
+                      "rate constants)"}
+
     if args.no_e2e:
         if rank == 0:
             print(json.dumps({"profiling_run": True, "value": value, "ms_per_step": total_ms / args.steps,
@@ -354,6 +366,14 @@ def run_ours(args):
     # ================================================================== sharding self-check (N > 1)
     sharding = None
     if world > 1:
+        # While rank 0 works alone the other ranks must wait on the HOST: an NCCL barrier would park a spinning kernel on
+        # their GPUs, and rank 0's own kernels on those GPUs (another context) would then be time-sliced against it.
+        host_pg = dist.new_group(backend="gloo")
+
+        def host_barrier():
+            torch.cuda.synchronize()
+            dist.barrier(group=host_pg)
+
         barrier()
         if rank == 0:
             one = pkg.host.Frontend(abi.CudaBackend(device_ids=[local]))
@@ -362,7 +382,7 @@ def run_ours(args):
             t_one = time.perf_counter() - t0
             eq = bool(np.array_equal(Y1.view(np.uint64), Yfull.view(np.uint64)))
             sharding = {"gathered_ranks_equal_single_device_bitwise": eq, "single_device_s": t_one}
-        barrier()
+        host_barrier()
         if rank == 0:
             # the library's own in-process split (north_star: one host thread + stream per device, host-side gather)
             multi = pkg.host.Frontend(abi.CudaBackend(device_ids=list(range(world))))
@@ -374,6 +394,7 @@ def run_ours(args):
             sharding.update({"library_sharded_n_devices": world, "library_sharded_solves_per_s": S / t_n,
                              "library_sharded_s": t_n,
                              "library_sharded_equals_single_device_bitwise": bool(np.array_equal(Yn.view(np.uint64), Y1.view(np.uint64)))})
+        host_barrier()
         barrier()
 
     # ================================================================== second workload: configs[1], one replica per rank
@@ -442,7 +463,7 @@ def run_ours(args):
                         "c_abi_pinned_value": abi_value, "c_abi_matches_resident_run": same},
                 "gpu_launches": res["launches"], "clocks": clocks, "nan_sets_rank0": int(nan.sum()),
                 "wall_s_timed_region": res["wall"],
-                "sharding_check": sharding,
+                "sharding_check": sharding, "limits": limits,
                 "configs1": {"workload": "configs[1]: pdesolver over all 5000 rows of parameter_ensemble.csv, run_ensemble defaults "
                                          "(dr=0.2/Nr=50, tf=5, Nts=100, tol=1e-4, maxit=20), full snapshot output (2.52 GB per pass); "
                                          "one replica per rank (weak)",

@@ -852,12 +852,13 @@ int gab1_solve_batch(const gab1_opts* o, int64_t S, const double* Co, int64_t Co
   const int64_t nout = gab1_out_doubles_per_set(o);
   const char* plan_env = getenv("GAB1_SHARD_PLAN");       // contiguous | dealt (A/B measurements, tests)
   const bool dealt = plan_env && plan_env[0] ? strcmp(plan_env, "dealt") == 0 : nout <= kDealtMaxDoubles;
+  std::vector<int64_t> perm;          // outlives the worker threads, which are joined below
   if (dealt) {
     // Small per-set outputs (final profiles, six scalars, one percentage): the sets are dealt to the devices from the
     // descending step-count order, so that every device receives the same mix of long and short solves (and of the
     // diverging ones, which are cheap) whatever the order of the caller's matrix; each device's sets are gathered into
     // contiguous staging rows, solved as one local batch, and scattered back to their columns.
-    std::vector<int64_t> perm((size_t)S);
+    perm.resize((size_t)S);
     gab1_deal_shards(S, dt, o->tf, nd, perm.data(), bounds.data());
     for (int g = 0; g < nd; ++g)
       th.emplace_back([&, g]() {

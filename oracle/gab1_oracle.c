@@ -6,12 +6,17 @@
  * and as the timed CPU baseline (bench.py cpu_baseline / --impl reference).  Nothing in the
  * shipped library links, imports or calls this file.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or stored solver outputs, and no
- * Julia runtime exists in the build image or on the GPU box, so this restatement cannot be checked
- * against outputs of the reference itself.  It is pinned instead by (i) a second independent NumPy
- * restatement that must agree bit-for-bit (oracle/numpy_oracle.py, tests/test_oracle_cross.py),
- * (ii) exact discrete invariants of the scheme, (iii) the analytic steady aSFK profile and the
- * experimental % SHP2-bound GAB1 the reference was fitted to (tests/test_oracle_physics.py).
+ * PARITY PIN.  The reference ships no tests and no bit-level golden vectors, and no Julia runtime exists in the build
+ * image or on the GPU box, so this restatement cannot be compared with the reference solver output value by value.
+ * What the reference tree does hold is output COMPUTED BY ITS SOLVER: the eFAST sensitivity indices of
+ * `GSA results/eFAST-GSA-res_concs_1000-spls-per-param_{S1,ST}.csv` (+ the `_memb-SFKs` pair), produced by
+ * `gsa(fbatch_concs_mt, eFAST(), pbounds; samples=1000, batch=true)` (GSA_concs.jl:50-97) through sapdesolver /
+ * sapdesolver_membSFK — functionals of 5000 full-length solves each.  This oracle reproduces them within the spread over
+ * the design's random phases, including which outputs are exactly constant (tests/test_efast_pin.py; eFAST itself is
+ * restated in oracle/efast.py from GlobalSensitivity 2.1.3).  That is a coarse pin (1e-2, not 1e-9): at the 1e-9 level
+ * the oracle is additionally held by (i) a second independent NumPy restatement that must agree bit for bit
+ * (oracle/numpy_oracle.py, tests/test_oracle_cross.py), (ii) exact discrete invariants of the scheme, (iii) the analytic
+ * steady aSFK profile and the experimental % SHP2-bound GAB1 the reference was fitted to (tests/test_oracle_physics.py).
  *
  * What it follows (all under the reference's Julia/ directory):
  *   pdesolver                basepdesolver.jl:25-312

@@ -2,7 +2,7 @@
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs import this.  `OracleBackend` has the same
 `.solve` shape as the product's CudaBackend so that the Julia-surface frontend can be bound to either and the
-results compared.  PARITY UNPINNED (no reference outputs exist; see the header of gab1_oracle.c).
+results compared.  Parity pin: the reference's stored eFAST indices (coarse) — see the header of gab1_oracle.c.
 """
 from __future__ import annotations
 
