@@ -46,8 +46,11 @@ struct GangLayout {
   static constexpr int OFF_CTAB = KN * NCY * 32;       // c+ / c- per slot: [i][2][G]
   static constexpr int OFF_XCH = OFF_CTAB + 2 * KN * G;
   static constexpr int OFF_TAB = OFF_XCH + NS * XS;
-  static constexpr int OFF_DUMMY = OFF_TAB + NT * 32;  // [species][lane]: where a slot update goes when it must not land
-  static constexpr int OFF_ROWS = OFF_DUMMY + NCY * 32;  // + 2 * P_pad staged rows
+  // scratch: [species][lane] lines where a slot update goes when it must not land (time loop), and the two staged rows of
+  // the output writers (rare path, epilogue) — never live at the same time, so they share the space
+  static constexpr int OFF_DUMMY = OFF_TAB + NT * 32;
+  static constexpr int OFF_ROWS = OFF_DUMMY;
+  static __host__ __device__ constexpr int doubles(int P_pad) { return OFF_DUMMY + (NCY * 32 > 2 * P_pad ? NCY * 32 : 2 * P_pad); }
 };
 
 // value of species q at node n (0..Nr; node 0 mirrors node 1) of gang s

@@ -17,7 +17,7 @@ int launch(const KernelArgs& args, int device, cudaStream_t stream) {
   static int blocks_per_sm[64] = {0};
   static int sms[64] = {0};
   using L = GangLayout<G, KN>;
-  const size_t smem = ((size_t)L::OFF_ROWS + 2 * (size_t)args.P_pad) * sizeof(double);
+  const size_t smem = (size_t)L::doubles(args.P_pad) * sizeof(double);
   auto kern = gang_kernel<G, KN, MODE>;
   {
     std::lock_guard<std::mutex> lk(mu);

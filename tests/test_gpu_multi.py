@@ -1,5 +1,5 @@
-"""The library's own multi-GPU path (gab1_solve_batch / gab1_solve_tangent with n_devices > 1: contiguous shards balanced by
-step count, one host thread and stream per device, no collective).  Needs at least two visible GPUs; skipped otherwise
+"""The library's own multi-GPU path (gab1_solve_batch / gab1_solve_tangent with n_devices > 1: shards balanced by step count —
+dealt for small per-set outputs, contiguous for full snapshots — one host thread and stream per device, no collective).  Needs at least two visible GPUs; skipped otherwise
 (`gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`)."""
 import numpy as np
 import pytest
@@ -31,6 +31,25 @@ def test_sharded_solve_is_bitwise_the_single_device_solve(pkg, ndev, ensemble):
     six1 = one.sapdesolver_batch(Co, D, k, tf=0.3, out_mode=pkg.abi.OUT_SIX)
     six2 = pkg.host.Frontend(pkg.abi.CudaBackend(n_devices=2)).sapdesolver_batch(Co, D, k, tf=0.3, out_mode=pkg.abi.OUT_SIX)
     np.testing.assert_array_equal(six1.out, six2.out)
+
+
+@pytest.mark.parametrize("plan", ["dealt", "contiguous"])
+def test_both_shard_plans_scatter_every_set_to_its_own_row(pkg, ndev, ensemble, plan, monkeypatch):
+    """Small per-set outputs are sharded by dealing the descending step-count order (gather, local batch, scatter); the
+    contiguous plan is forced onto the same call for comparison.  Ragged work (a per-set dt that makes some sets 4x longer),
+    per-set Co, every diagnostic array: each must come back in the caller's row order, bit-identical to one device."""
+    monkeypatch.setenv("GAB1_SHARD_PLAN", plan)
+    g = np.random.Generator(np.random.PCG64(3))
+    D, k = ensemble[:1501, :7], ensemble[:1501, 7:]
+    Co = pkg.params.base_Co()[None, :] * g.uniform(0.5, 2.0, size=(1501, 1))
+    dt = pkg.params.default_dt(D, k, 0.2) * np.where(g.random(1501) < 0.2, 0.25, 1.0)
+    kw = dict(dr=0.2, tf=0.3, dt=dt, out_mode=pkg.abi.OUT_FINAL_STATE)
+    ref = pkg.host.Frontend(pkg.abi.CudaBackend(n_devices=1)).sapdesolver_batch(Co, D, k, **kw)
+    for n in sorted({2, ndev}):
+        res = pkg.host.Frontend(pkg.abi.CudaBackend(device_ids=list(range(n)))).sapdesolver_batch(Co, D, k, **kw)
+        assert np.array_equal(res.out.view(np.uint64), ref.out.view(np.uint64)), f"{plan}, {n} devices"
+        for f in ("status", "n_saved", "n_steps", "n_bc_iters"):
+            np.testing.assert_array_equal(getattr(res, f), getattr(ref, f))
 
 
 def test_sharded_tangent_is_bitwise_the_single_device_tangent(pkg, ndev, ensemble):
