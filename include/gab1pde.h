@@ -209,7 +209,7 @@ int gab1_deal_shards(int64_t S, const double* dt, double tf, int32_t n_shards, i
  *   matrices   bit m set => matrix m (GAB1_M_*), a subset of o->matrix_mask; o->out_mode must be GAB1_OUT_FULL
  *   q          [matrix (ascending m)][i][c - c0][node], doubles
  *   n_valid    number of sets that entered the statistics
- * At most 25600 sets per call (one row of all sets is sorted in shared memory).
+ * At most 16384 sets per call (one row of all sets, padded to a power of two, is sorted in 200 KB of shared memory).
  *
  * gab1_solve_ensemble_quantiles: HOST buffers; solves the ensemble on one GPU (o->device_ids[0], default 0), keeps the full
  * result in HBM and returns only the statistics and the per-set diagnostics — 0.5 MB per set never crosses PCIe.

@@ -286,6 +286,12 @@ class CudaBackend:
         self.arith = arith
         self.device_ids = None if device_ids is None else (C.c_int32 * len(device_ids))(*device_ids)
 
+    def strict_twin(self):
+        """The same devices with arith = 1 (every operation of the reference in source order: bit-identical to the oracle)."""
+        t = CudaBackend(self.n_devices, ARITH_STRICT)
+        t.device_ids = self.device_ids
+        return t
+
     def _bind(self, o: Opts):
         o.n_devices = self.n_devices
         o.device_ids = None if self.device_ids is None else C.cast(self.device_ids, C.POINTER(C.c_int32))

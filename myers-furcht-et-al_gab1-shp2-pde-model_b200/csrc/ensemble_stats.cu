@@ -135,7 +135,8 @@ int ensemble_quantiles_device(const gab1_opts* o, int device, cudaStream_t strea
   while (N2 < S) N2 <<= 1;
   const size_t budget = 200 * 1024;
   if ((size_t)N2 * sizeof(double) > budget)
-    return fail(-6, "ensemble quantiles hold one row of all sets in shared memory: at most %zu sets per call", budget / sizeof(double));
+    return fail(-6, "ensemble quantiles sort one row of all sets in shared memory, padded to a power of two: at most 16384 sets per call "
+                    "(%lld requested)", S);
   int NT = (int)(budget / ((size_t)N2 * sizeof(double)));
   if (NT > 4) NT = 4;
   a.N2 = N2; a.NT = NT;

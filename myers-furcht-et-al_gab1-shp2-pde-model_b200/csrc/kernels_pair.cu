@@ -65,18 +65,28 @@ int launch_group16_kernel(int K, int variant, int mode, bool mirror, const Kerne
   switch (K) {
     case 1: return GAB1_LAUNCH_V(1, true, false);
     case 2: return GAB1_LAUNCH_V(2, true, false);
+#ifdef GAB1_BUILD_AB_VARIANTS
     case 4: return variant == 1 ? GAB1_LAUNCH_V(4, false, false) : GAB1_LAUNCH_V(4, true, false);
+#else
+    case 4: if (variant == 0) return GAB1_LAUNCH_V(4, true, false); break;
+#endif
   }
+  if (variant != 0) return fail(-6, "the plain / token loop variants are A/B builds (-DGAB1_BUILD_AB_VARIANTS)");
   return fail(-6, "no 16-lane kernel for K=%d", K);
 }
 #else
 // one parameter set per warp: K nodes per lane
 int launch_group32_kernel(int K, int variant, int mode, bool mirror, const KernelArgs& a, int device, cudaStream_t stream) {
   switch (K) {
+#ifdef GAB1_BUILD_AB_VARIANTS
     case 2: return variant == 2 ? GAB1_LAUNCH_V(2, false, true) : variant == 1 ? GAB1_LAUNCH_V(2, false, false) : GAB1_LAUNCH_V(2, true, false);
+#else
+    case 2: if (variant == 0) return GAB1_LAUNCH_V(2, true, false); break;
+#endif
     case 4: return GAB1_LAUNCH_V(4, true, false);
     case 8: return GAB1_LAUNCH_V(8, true, false);
   }
+  if (variant != 0) return fail(-6, "the plain / token loop variants are A/B builds (-DGAB1_BUILD_AB_VARIANTS)");
   return fail(-6, "no 32-lane kernel for K=%d", K);
 }
 #endif

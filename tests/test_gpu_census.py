@@ -89,6 +89,15 @@ def test_census_config2_synthetic_priors(pkg, gfe, ofe):
         s = sfe.sapdesolver_batch(Co, ens[bad, :7], ens[bad, 7:], out_mode=pkg.abi.OUT_FINAL_STATE, **kw)
         same = (s.out.view(np.uint64) == ref.out[bad].view(np.uint64)) | (np.isnan(s.out) & np.isnan(ref.out[bad]))
         assert same.all() and np.array_equal(s.n_bc_iters, ref.n_bc_iters[bad]) and np.array_equal(s.status, ref.status[bad])
+    # certify=True (host.Frontend._certify): the sets that respond to a one-ulp input change are found by the library
+    # itself and re-solved strictly, after which EVERY live set — no exemption — is within 1e-9 with the oracle's control flow
+    cert = gfe.sapdesolver_batch(Co, ens[:, :7], ens[:, 7:], out_mode=pkg.abi.OUT_FINAL_STATE, certify=True, **kw)
+    rep_c = census(cert, ref, name="config2_2048_prior_draws_certified")
+    rep_c["resolved_strict"] = [int(i) for i in cert.resolved_strict]
+    check(rep_c)
+    live_ill = set(np.flatnonzero(ill & ((ref.status & 1) == 0)).tolist())
+    assert live_ill <= set(rep_c["resolved_strict"]), (live_ill, rep_c["resolved_strict"])
+    assert len(cert.resolved_strict) <= 60, "the certification should re-solve a few per cent of the draws at most"
     six = gfe.sapdesolver_batch(Co, ens[:, :7], ens[:, 7:], out_mode=pkg.abi.OUT_SIX, **kw)
     six_ref = ofe.sapdesolver_batch(Co, ens[:, :7], ens[:, 7:], out_mode=pkg.abi.OUT_SIX, **kw)
     np.testing.assert_array_equal(six.status[~ill], six_ref.status[~ill])

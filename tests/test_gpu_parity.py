@@ -288,10 +288,7 @@ FAMILIES = {
     # not only the one the dispatcher picks for a grid (gab1pde.cu: pick_fast)
     "legacy": [0.4, 0.2, 0.1],
     "group16": [0.4, 0.25, 0.2],
-    "group16p": [0.2],
     "group32": [0.2, 0.1, 0.05],
-    "group32p": [0.2],
-    "group32t": [0.2],
     # state in shared memory (stream_kernel.cuh): K = 4, 8, 16 nodes per lane; dr = 0.025 (Nr = 400) exists only here
     "stream": [0.2, 0.1, 0.05, 0.025],
     # latency path: one CTA of 2 / 4 / 7 warps per set (team_kernel.cuh)
