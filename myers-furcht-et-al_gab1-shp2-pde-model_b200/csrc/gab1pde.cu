@@ -179,6 +179,58 @@ int solve_with_gangs(const GangPick& gp, int mode, gab1::KernelArgs a, const Wor
            : gab1::launch_stream_kernel(16, mode, b, device, stream);
 }
 
+// ---- the latency lane (duo_kernel.cuh): which sets of a batch get two warps ------------------------------------------
+// Decided on the device from the sorted step counts, so the host never waits: the first n sets of the descending-work
+// queue get two warps each (queue [0, n), counter[5] / counter[4]) and the one-set-per-warp queue starts at n (counter[0]).  Both kernels give the same bits for a set, so n is free to follow the load:
+//   S > warps        the batch fills the GPU: only sets whose step count exceeds half the per-warp share of the whole batch
+//                    (they would still be running when everything else has finished), at most one per two SMs;
+//   warps/2 < S      every set has a warp to itself: the sets within 1.6x (the duo's gain) of the longest one, as far as the
+//                    registers they take from the other kernel allow (a duo CTA displaces a four-warp CTA);
+//   S <= warps/2     every set.
+__global__ void __launch_bounds__(1024) duo_plan_kernel(long long S, const unsigned* keys, long long warps, int nsm, int all,
+                                                        unsigned* counter) {
+  __shared__ unsigned long long s_part[32];
+  __shared__ unsigned long long s_total;
+  __shared__ unsigned s_cnt;
+  const int tid = threadIdx.x;
+  unsigned long long acc = 0;
+  for (long long i = tid; i < S; i += 1024) acc += keys[i];
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((tid & 31) == 0) s_part[tid >> 5] = acc;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long tot = 0;
+    for (int i = 0; i < 32; ++i) tot += s_part[i];
+    s_total = tot;
+  }
+  __syncthreads();
+  double thr;
+  long long cap;
+  if (all) { thr = -1.0; cap = S; }
+  else if (S > warps) { thr = 0.5 * (double)s_total / (double)warps; cap = nsm / 2; }
+  else if (2 * S > warps) { thr = 0.625 * (double)keys[0]; cap = (warps - S) / 4; }
+  else { thr = -1.0; cap = S; }
+  const long long lim = S < cap ? S : cap;
+  unsigned local = 0;
+  for (long long i = tid; i < lim; i += 1024) local += ((double)keys[i] > thr) ? 1u : 0u;
+  if (local) atomicAdd(&s_cnt, local);
+  __syncthreads();
+  if (tid == 0) { counter[0] = s_cnt; counter[4] = s_cnt; counter[5] = 0u; }
+}
+
+// The plan, then ONE launch: the one-set-per-warp kernel with the latency lane in front (duo_kernel.cuh: duo_solve_kernel).
+int solve_with_duo(int K, int mode, gab1::KernelArgs a, const Workspace& w, int device, cudaStream_t stream, bool all) {
+  int nsm = 148;
+  CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+  duo_plan_kernel<<<1, 1024, 0, stream>>>(a.S, w.keys_out, (long long)nsm * 8, nsm, all ? 1 : 0, w.counter);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  a.dyn_count = w.counter + 4;
+  a.duo_counter = w.counter + 5;
+  return gab1::launch_duo_kernel(K, mode, a, device, stream);
+}
+
 int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long S, const double* Co, long long Co_stride,
                  const double* D, const double* k, const double* dt, const double* r, double* out, int* status,
                  int* n_saved, long long* n_steps, long long* n_bc, void* workspace) {
@@ -207,7 +259,7 @@ int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long 
   a.R_pow3 = pow(o->R, 3.0);
   a.P_pad = (o->Nr + 1 + 3) & ~3;
 
-  CUDA_TRY(cudaMemsetAsync(w.counter, 0, 4 * sizeof(unsigned), stream));
+  CUDA_TRY(cudaMemsetAsync(w.counter, 0, 8 * sizeof(unsigned), stream));
   {
     const int tb = 256;
     work_keys_kernel<<<(unsigned)((S + tb - 1) / tb), tb, 0, stream>>>(S, dt, o->tf, w.keys_in, w.vals_in, r, o->dr,
@@ -276,6 +328,15 @@ int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long 
                                : gab1::launch_group32_kernel(fp.K, fp.variant, mode, mirror, a, device, stream);
     if (rc || mirror) return rc;
     a.guard_expect = 1;          // the general kernel below runs only if the pair kernel declined the grid
+  }
+  // ---- the latency lane: two warps for the sets that would outlast the batch, or for all of a small batch (duo_kernel.cuh;
+  //      bit-identical to the kernel below).  GAB1_KERNEL=duo sends every set there, GAB1_KERNEL=legacy or GAB1_DUO=0 none.
+  if (mode != gab1::MODE_STRICT && !fp.K && (K == 2 || K == 4)) {
+    const char* e = getenv("GAB1_KERNEL");
+    const char* d = getenv("GAB1_DUO");
+    const bool all = e && strcmp(e, "duo") == 0;
+    const bool off = (e && e[0] && !all) || (d && d[0] == '0');
+    if (!off) return solve_with_duo(K, mode, a, w, device, stream, all);
   }
   return gab1::launch_single_kernel(K, mode, a, device, stream);
 }

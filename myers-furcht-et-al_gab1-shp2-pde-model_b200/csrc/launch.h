@@ -26,6 +26,7 @@ struct KernelArgs {
   unsigned int* retry_count;
   int* retry_list;
   const unsigned int* dyn_count;
+  unsigned int* duo_counter; // queue head of the latency lane (duo_kernel.cuh): its items are [0, *dyn_count)
 };
 
 enum { MODE_FAST_FOR = 0, MODE_FAST_WHILE = 1, MODE_STRICT = 2 };
@@ -52,6 +53,9 @@ int launch_group32_kernel(int K, int variant, int mode, bool mirror, const Kerne
 int launch_stream_kernel(int K, int mode, const KernelArgs& args, int device, cudaStream_t stream);
 // latency kernel (team_kernel.cuh): one CTA of ceil(Nr/32) warps per set, 32 < Nr <= 256, fast modes only
 int launch_team_kernel(int mode, const KernelArgs& args, int device, cudaStream_t stream);
+// the one-set-per-warp kernel with the latency lane in front (duo_kernel.cuh): two warps per set for items [0, *args.dyn_count)
+// of the queue (head: args.duo_counter), one warp per set from *args.counter on; K in {2, 4}, fast modes only
+int launch_duo_kernel(int K, int mode, const KernelArgs& args, int device, cudaStream_t stream);
 // several sets per warp (gang_kernel.cuh): G lanes per set (one translation unit per G), KN node slots per lane
 int launch_gang_kernel_g2(int KN, int mode, const KernelArgs& args, int device, cudaStream_t stream);
 int launch_gang_kernel_g4(int KN, int mode, const KernelArgs& args, int device, cudaStream_t stream);

@@ -293,6 +293,8 @@ FAMILIES = {
     "stream": [0.2, 0.1, 0.05, 0.025],
     # latency path: one CTA of 2 / 4 / 7 warps per set (team_kernel.cuh)
     "team": [0.25, 0.2, 0.1, 0.05],
+    # latency lane of the register-resident grids: two warps per set (duo_kernel.cuh), K = 2 / 2 / 4
+    "duo": [0.25, 0.2, 0.1],
     # several sets per warp, G lanes per set, the state in shared memory (gang_kernel.cuh): the default for Nr > 128;
     # G = 2 / 4 / 4 / 8 / 16 / 32 on these grids
     "gang": [0.4, 0.25, 0.2, 0.1, 0.05, 0.025],
@@ -333,6 +335,43 @@ def test_every_kernel_family_matches_the_oracle(pkg, gfe, ofe, ensemble, family,
                 assert rel_err(res.out[:, 4:], ref.out[:, 4:]) < RTOL
             else:
                 assert rel_err(res.out, ref.out) < RTOL
+
+
+def test_duo_kernel_is_bit_identical_to_the_one_warp_kernel(pkg, gfe, ensemble, monkeypatch):
+    """The dispatcher sends any subset of a batch to the two-warps-per-set kernel (gab1pde.cu: duo_plan_kernel), which is only
+    sound because that kernel evaluates the one-set-per-warp kernel's expressions in the same order: values, NaN patterns,
+    iteration counts and status words must agree BIT FOR BIT — on posterior rows, on wide prior draws (diverging sets, sets that
+    run into the iteration limit step after step), in both loop forms, on every output mode and on a K = 4 grid."""
+    abi = pkg.abi
+    Co = pkg.params.base_Co()
+    prior = pkg.params.synthetic_prior_ensemble(192, seed=77)
+    rows = np.r_[0:24, 2500:2508, 4990:5000]
+    cases = []
+    for variant in ("pdesolver", "rect", "pulsechase", "membSFK", "rect_frozen_modulus", "fitting_mask"):
+        cases.append(("pdesolver_batch", Co, ensemble[rows], dict(dr=0.2, tf=0.7, Nts=9, tol=1e-4, maxiters=20, **VARIANTS[variant])))
+    cases.append(("pdesolver_batch", Co, ensemble[rows[:12]], dict(dr=0.1, tf=0.2, Nts=5, tol=1e-4, maxiters=20)))
+    cases.append(("pdesolver_batch", Co, ensemble[rows], dict(dr=0.2, tf=1.0, Nts=10, tol=1e-4, maxiters=20, out_mode=abi.OUT_PCT_BOUND)))
+    cases.append(("pdesolver_batch", Co, prior, dict(dr=0.2, tf=5.0, Nts=4, tol=1e-4, maxiters=20)))
+    for mode in (abi.OUT_SIX, abi.OUT_FINAL4, abi.OUT_FINAL_STATE):
+        cases.append(("sapdesolver_batch", Co, prior, dict(dr=0.2, tf=5.0, out_mode=mode)))
+        cases.append(("sapdesolver_batch", pkg.params.hela_Co(), prior, dict(dr=0.2, tf=2.0, membSFK=True, out_mode=mode)))
+    cases.append(("sapdesolver_batch", Co, prior[:48], dict(dr=0.1, tf=0.5, out_mode=abi.OUT_FINAL_STATE)))
+    for fn, co, ens, kw in cases:
+        got = {}
+        for family in ("legacy", "duo"):
+            monkeypatch.setenv("GAB1_KERNEL", family)
+            got[family] = getattr(gfe, fn)(co, ens[:, :7], ens[:, 7:], **kw)
+        a, b = got["legacy"], got["duo"]
+        assert_bits(a.out, b.out, f"{fn} {kw}")
+        check_control_flow(b, a)
+    # the automatic split (the head of the descending-work queue on two warps, the rest on one) changes nothing either
+    monkeypatch.delenv("GAB1_KERNEL")
+    big = pkg.params.synthetic_prior_ensemble(1500, seed=78)
+    auto = gfe.sapdesolver_batch(Co, big[:, :7], big[:, 7:], dr=0.2, tf=5.0, out_mode=abi.OUT_SIX)
+    monkeypatch.setenv("GAB1_DUO", "0")
+    plain = gfe.sapdesolver_batch(Co, big[:, :7], big[:, 7:], dr=0.2, tf=5.0, out_mode=abi.OUT_SIX)
+    assert_bits(auto.out, plain.out, "automatic split")
+    check_control_flow(auto, plain)
 
 
 def test_finest_grid_all_outputs_and_edge_cases(pkg, gfe, ofe, ensemble):
