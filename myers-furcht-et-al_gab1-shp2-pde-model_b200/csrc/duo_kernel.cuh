@@ -27,6 +27,8 @@
 //
 // Reference: basepdesolver.jl:149-296 (time loop), :150-180 (interior), :197-242 (membrane loop).
 #pragma once
+#include <stdio.h>
+
 #include <type_traits>
 
 #include "solver_kernel.cuh"
@@ -597,6 +599,23 @@ duo_solve_kernel(const KernelArgs a) {
       g.c0[i] = g.interior[i] ? c0 : 0.0;
     }
   }
+  // ---- isolation (a.isolate, full batches only): a warp of the latency lane keeps the warps it would share issue slots
+  //      with from taking new sets while its set runs.  Measured on B200: the longest set of the bench ensemble takes 248 ms
+  //      alone on the GPU and 312 ms next to a second resident warp on its scheduler — and bounds the 8-GPU run.
+  //      1: the whole SM is reserved; 2: the scheduler (%warpid mod 4) only.  Reservations are counters in global memory.
+  int* resv = nullptr;
+  if (a.isolate) {
+    unsigned smid, wid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+    resv = a.sm_resv + 4 * smid + (a.isolate == 2 ? (wid & 3u) : 0u);
+  }
+#ifdef GAB1_DUO_TIMING
+  unsigned long long tl0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl0));
+  atomicMin((unsigned long long*)(a.duo_counter + 3), tl0);      // counter words 8..9: earliest start (memset to 0xff by the host)
+  int tl_sets = 0;
+#endif
   // ---- latency lane: two warps per set ----
   const unsigned n_duo = *a.dyn_count;
   if (n_duo) {
@@ -607,13 +626,34 @@ duo_solve_kernel(const KernelArgs a) {
       const unsigned item = s_item[pair];
       if (item >= n_duo) break;
       const long long set = a.order ? (long long)a.order[item] : (long long)item;
+      if (resv && lane == 0) {
+        atomicAdd(resv, 1);
+        __threadfence();
+        if (roleA) atomicAdd(a.duo_counter + 1, 1u);      // this set's reservations are visible
+      }
       duo_solve_set<K, MODE>(a, set, lane, roleA, ws, dx, g, s_flags[pair], &s_bc[pair], bar0);
+      if (resv && lane == 0) atomicSub(resv, 1);
+#ifdef GAB1_DUO_TIMING
+      if (lane == 0 && roleA) {
+        unsigned long long tl1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl1));
+        printf("timeline duo item %u set %lld done at %.3f ms\n", item, set, (double)(tl1 - *(volatile unsigned long long*)(a.duo_counter + 3)) * 1e-6);
+      }
+#endif
     }
     if (roleA) ws[lane] = 0.0;        // the throughput kernel's header starts clean
     __syncwarp();
   }
   // ---- throughput lane: one warp per set; its queue starts behind the latency lane's sets ----
+  if (resv && n_duo) {
+    // the queue is in descending-work order, so the first set a warp takes is among the longest of the batch: no warp
+    // starts one before every set of the latency lane has been claimed and its reservation is visible (microseconds)
+    while (*(volatile unsigned*)(a.duo_counter + 1) < n_duo) __nanosleep(200);
+  }
   for (;;) {
+    if (resv) {                       // sleep while a set of the latency lane has this SM / scheduler reserved
+      while (*(volatile int*)resv > 0) __nanosleep(4000);
+    }
     unsigned item = 0;
     if (lane == 0) item = atomicAdd(a.counter, 1u);
     item = __shfl_sync(FULL, item, 0);
@@ -621,7 +661,17 @@ duo_solve_kernel(const KernelArgs a) {
     const long long set = a.order ? (long long)a.order[item] : (long long)item;
     solve_set<K, MODE>(a, set, lane, ws, g);
     __syncwarp();
+#ifdef GAB1_DUO_TIMING
+    ++tl_sets;
+#endif
   }
+#ifdef GAB1_DUO_TIMING
+  if (lane == 0) {
+    unsigned long long tl1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl1));
+    printf("timeline warp exit %.3f ms sets %d\n", (double)(tl1 - *(volatile unsigned long long*)(a.duo_counter + 3)) * 1e-6, tl_sets);
+  }
+#endif
 }
 
 }  // namespace gab1

@@ -147,10 +147,12 @@ size_t cub_bytes_for(long long S) {
   return bytes;
 }
 
+constexpr size_t kCounterBytes = 8192;   // 64 queue words + 4 reservation words for each of up to 496 SMs
+
 size_t carve(Workspace& w, void* base, long long S) {
   size_t off = 0;
   auto take = [&](size_t bytes) { void* p = base ? (char*)base + off : nullptr; off += align_up(bytes, 256); return p; };
-  w.counter = (unsigned*)take(256);     // [0] queue head, [1] guard word
+  w.counter = (unsigned*)take(kCounterBytes);     // [0] queue head, [1] guard word, [2..5] hand-over / latency lane, [64..] SM reservations
   w.keys_in = (unsigned*)take(sizeof(unsigned) * (size_t)S);
   w.keys_out = (unsigned*)take(sizeof(unsigned) * (size_t)S);
   w.vals_in = (int*)take(sizeof(int) * (size_t)S);
@@ -228,6 +230,13 @@ int solve_with_duo(int K, int mode, gab1::KernelArgs a, const Workspace& w, int 
   CUDA_TRY(cudaGetLastError());
   a.dyn_count = w.counter + 4;
   a.duo_counter = w.counter + 5;
+  if (getenv("GAB1_DUO_TIMELINE")) CUDA_TRY(cudaMemsetAsync(w.counter + 8, 0xff, 8, stream));   // timing builds: earliest start
+  // full batches: the few sets of the latency lane run isolated (duo_kernel.cuh); GAB1_ISOLATE = 0 | sm | sched overrides
+  a.sm_resv = (int*)(w.counter + 64);
+  a.isolate = (!all && a.S > (long long)nsm * 8 && (size_t)(64 + 4 * nsm) * sizeof(unsigned) <= kCounterBytes) ? 2 : 0;
+  if (const char* e = getenv("GAB1_ISOLATE")) {
+    if (a.isolate) a.isolate = strcmp(e, "sched") == 0 ? 2 : (strcmp(e, "sm") == 0 ? 1 : (e[0] == '0' ? 0 : a.isolate));
+  }
   return gab1::launch_duo_kernel(K, mode, a, device, stream);
 }
 
@@ -259,7 +268,7 @@ int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long 
   a.R_pow3 = pow(o->R, 3.0);
   a.P_pad = (o->Nr + 1 + 3) & ~3;
 
-  CUDA_TRY(cudaMemsetAsync(w.counter, 0, 8 * sizeof(unsigned), stream));
+  CUDA_TRY(cudaMemsetAsync(w.counter, 0, kCounterBytes, stream));
   {
     const int tb = 256;
     work_keys_kernel<<<(unsigned)((S + tb - 1) / tb), tb, 0, stream>>>(S, dt, o->tf, w.keys_in, w.vals_in, r, o->dr,

@@ -27,6 +27,8 @@ struct KernelArgs {
   int* retry_list;
   const unsigned int* dyn_count;
   unsigned int* duo_counter; // queue head of the latency lane (duo_kernel.cuh): its items are [0, *dyn_count)
+  int* sm_resv;              // 4 reservation counters per SM (duo_kernel.cuh: isolation of the latency lane's sets)
+  int isolate;               // 0: off, 1: a set of the latency lane reserves its SM, 2: its schedulers only
 };
 
 enum { MODE_FAST_FOR = 0, MODE_FAST_WHILE = 1, MODE_STRICT = 2 };

@@ -17,7 +17,7 @@ abi = pkg.abi
 
 
 def env(**kv):
-    for k in ("GAB1_KERNEL", "GAB1_DUO"):           # GAB1_CARVEOUT, if set by the caller, stays
+    for k in ("GAB1_KERNEL", "GAB1_DUO", "GAB1_ISOLATE"):
         os.environ.pop(k, None)
     for k, v in kv.items():
         os.environ[k] = v
@@ -59,21 +59,20 @@ def main():
                           "cycles_per_step_two_warps": ms2 * 1e-3 * 1.965e9 / nt[order[0]]}), flush=True)
 
     perm, bounds = abi.deal_shards(dt, 5.0, 8)
-    for g in (0, 3) if "shards" in which else ():
-        idx = perm[bounds[g]:bounds[g + 1]]
-        sh = ens[idx]
-        env(GAB1_DUO="0"); ms1, r1 = timed(fe, Co, sh, **kw)
-        env(); ms2, r2 = timed(fe, Co, sh, **kw)
-        print(json.dumps({"probe": "shard_of_8", "shard": g, "sets": int(len(idx)), "longest_steps": int(nt[idx].max()),
-                          "one_warp_only_ms": ms1, "with_latency_lane_ms": ms2, "gain": ms1 / ms2, "bit_identical": same(r1, r2),
-                          "ideal_ms_from_1gpu": 1962.6 / 8}), flush=True)
     perm4, bounds4 = abi.deal_shards(dt, 5.0, 4)
-    idx = perm4[bounds4[0]:bounds4[1]]
-    if "shards" in which:
-      env(GAB1_DUO="0"); ms1, r1 = timed(fe, Co, ens[idx], reps=2, **kw)
-      env(); ms2, r2 = timed(fe, Co, ens[idx], reps=2, **kw)
-      print(json.dumps({"probe": "shard_of_4", "sets": int(len(idx)), "one_warp_only_ms": ms1, "with_latency_lane_ms": ms2,
-                      "gain": ms1 / ms2, "bit_identical": same(r1, r2), "ideal_ms_from_1gpu": 1962.6 / 4}), flush=True)
+    shards = [("shard_0_of_8", perm[bounds[0]:bounds[1]], 1962.6 / 8), ("shard_3_of_8", perm[bounds[3]:bounds[4]], 1962.6 / 8),
+              ("shard_0_of_4", perm4[bounds4[0]:bounds4[1]], 1962.6 / 4)]
+    for name, idx, ideal in shards if "shards" in which else ():
+        sh = ens[idx]
+        rec = {"probe": name, "sets": int(len(idx)), "longest_steps": int(nt[idx].max()), "ideal_ms_from_1gpu": ideal}
+        env(GAB1_DUO="0"); ms0, r0 = timed(fe, Co, sh, **kw)
+        rec["one_warp_only_ms"] = ms0
+        for label, e in (("lane_no_isolation_ms", dict(GAB1_ISOLATE="0")), ("lane_sm_reserved_ms", dict(GAB1_ISOLATE="sm")),
+                         ("lane_scheduler_reserved_ms", dict(GAB1_ISOLATE="sched"))):
+            env(**e); ms, r = timed(fe, Co, sh, **kw)
+            rec[label] = ms
+            rec["bit_identical"] = rec.get("bit_identical", True) and same(r0, r)
+        print(json.dumps(rec), flush=True)
 
     # small batches of posterior rows (run_ensemble-sized and below), full length
     post = pkg.params.load_parameter_ensemble()
