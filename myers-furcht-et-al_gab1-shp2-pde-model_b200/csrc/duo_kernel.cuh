@@ -659,10 +659,21 @@ duo_solve_kernel(const KernelArgs a) {
     item = __shfl_sync(FULL, item, 0);
     if ((long long)item >= a.S) break;
     const long long set = a.order ? (long long)a.order[item] : (long long)item;
+#ifdef GAB1_DUO_TIMING
+    unsigned long long tls;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tls));
+#endif
     solve_set<K, MODE>(a, set, lane, ws, g);
     __syncwarp();
 #ifdef GAB1_DUO_TIMING
     ++tl_sets;
+    if (lane == 0) {
+      unsigned long long tle;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tle));
+      const unsigned long long t00 = *(volatile unsigned long long*)(a.duo_counter + 3);
+      if (tle - tls > 40000000ull || tle - t00 > 255000000ull)
+        printf("timeline set %lld item %u start %.3f end %.3f ms\n", set, item, (double)(tls - t00) * 1e-6, (double)(tle - t00) * 1e-6);
+    }
 #endif
   }
 #ifdef GAB1_DUO_TIMING

@@ -21,7 +21,8 @@ ok = (res.status & 1) == 0
 print("nan sets", (~ok).sum(), "bc/step of live", res.n_bc_iters[ok].sum() / res.n_steps[ok].sum())
 o = np.argsort(-res.n_steps)
 print("passes per step of the 12 longest:", (res.n_bc_iters[o[:12]] / res.n_steps[o[:12]]).round(2), res.status[o[:12]])
+np.savez("gpurun_out/r2s_shard0.npz", steps=res.n_steps, bc=res.n_bc_iters, status=res.status)
 PY
 grep -c "warp exit" gpurun_out/r2s_timeline.txt; grep "duo item\|^ms\|top steps\|nan sets\|passes per" gpurun_out/r2s_timeline.txt | head -20
 grep "warp exit" gpurun_out/r2s_timeline.txt | awk '{print $4}' | sort -n | awk '{a[NR]=$1} END {print "exit times ms: min", a[1], "p10", a[int(NR*0.1)], "p50", a[int(NR*0.5)], "p90", a[int(NR*0.9)], "p99", a[int(NR*0.99)], "max", a[NR]}'
-grep "warp exit" gpurun_out/r2s_timeline.txt | sort -k4 -n | tail -8
+grep "timeline set" gpurun_out/r2s_timeline.txt | sort -k9 -n | tail -40
