@@ -175,6 +175,23 @@ int gab1_solve_batch(const gab1_opts* o, int64_t S,
                      int64_t* n_steps, int64_t* n_bc_iters);
 
 /*
+ * gab1_solve_batch with the 1e-9 contract certified for every non-diverging set, ill-conditioned ones included (opt-in,
+ * about 2.3x the cost).  The fast kernels sit ~100 ulps of accumulated rounding from the reference's arithmetic; a set whose
+ * final state responds to a ONE-ulp change of the initial concentrations by `response` or more (relative; <= 0 selects the
+ * default 1e-12), or whose control flow responds at all, is re-solved with the strict kernels (arith = 1, every operation
+ * of basepdesolver.jl:150-242 in source order) and its rows replaced.  Same buffers as gab1_solve_batch, plus
+ *   resolved    S flags, 1 = the set was re-solved strictly   (may be NULL)
+ *   n_resolved  their number                                  (may be NULL)
+ * With o->arith == 1 this is gab1_solve_batch.
+ */
+int gab1_solve_batch_certified(const gab1_opts* o, int64_t S,
+                               const double* Co, int64_t Co_stride,
+                               const double* D, const double* k, const double* dt, const double* r,
+                               double* out, int32_t* status, int32_t* n_saved,
+                               int64_t* n_steps, int64_t* n_bc_iters,
+                               double response, int32_t* resolved, int64_t* n_resolved);
+
+/*
  * Same computation with every buffer already resident on CUDA device `device`
  * (device pointers), enqueued on `stream` (a cudaStream_t passed as void*; NULL = default
  * stream) without synchronising.  `workspace` must hold gab1_workspace_bytes(S) bytes of

@@ -205,6 +205,8 @@ def load_library():
     lib = C.CDLL(str(p))
     lib.gab1_solve_batch.argtypes = SOLVE_ARGTYPES
     lib.gab1_solve_batch.restype = C.c_int
+    lib.gab1_solve_batch_certified.argtypes = SOLVE_ARGTYPES + [C.c_double, _i32p, C.POINTER(C.c_int64)]
+    lib.gab1_solve_batch_certified.restype = C.c_int
     lib.gab1_solve_batch_device.argtypes = [C.POINTER(Opts), C.c_int32, C.c_void_p, C.c_int64,
                                             C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -309,6 +311,24 @@ class CudaBackend:
         if rc != 0:
             raise Gab1Error(f"gab1_solve_batch failed ({rc}): {lib.gab1_last_error().decode(errors='replace')}")
         return out, status, n_saved, n_steps, n_bc
+
+    def solve_certified(self, o: Opts, Co, D, k, dt, r, response: float = 0.0):
+        """gab1_solve_batch_certified: the fast solve, then a strict re-solve of every set whose final state responds to a
+        one-ulp change of Co.  Returns (out, status, n_saved, n_steps, n_bc, indices of the re-solved sets)."""
+        lib = load_library()
+        self._bind(o)
+        o.arith = self.arith
+        S = np.asarray(D).reshape(-1, N_D).shape[0]
+        resolved = np.zeros(S, dtype=np.int32)
+        n_res = C.c_int64(0)
+        rc, out, status, n_saved, n_steps, n_bc = call_solve(lib.gab1_solve_batch_certified, o, Co, D, k, dt, r,
+                                                             C.c_double(response), _ptr(resolved, _i32p), C.byref(n_res),
+                                                             alloc_out=self._alloc_out)
+        if rc != 0:
+            raise Gab1Error(f"gab1_solve_batch_certified failed ({rc}): {lib.gab1_last_error().decode(errors='replace')}")
+        idx = np.flatnonzero(resolved)
+        assert len(idx) == n_res.value
+        return out, status, n_saved, n_steps, n_bc, idx
 
     def solve_tangent(self, o: Opts, Co, D, k, dt, seeds, r):
         """Values and forward-mode partials along the seed directions (gab1_solve_tangent)."""

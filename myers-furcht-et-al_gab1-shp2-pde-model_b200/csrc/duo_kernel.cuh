@@ -563,7 +563,7 @@ __device__ void duo_solve_set(const KernelArgs& a, long long set, int lane, bool
 template <int K, int MODE>
 __global__ void __launch_bounds__(128, 2)
 duo_solve_kernel(const KernelArgs a) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   __shared__ unsigned s_item[2];
   __shared__ int s_flags[2][2];       // per pair: [0] the state is all NaN, [1] warp B's status bits
   __shared__ long long s_bc[2];       // per pair: warp B's membrane iteration count

@@ -184,8 +184,11 @@ int solve_with_gangs(const GangPick& gp, int mode, gab1::KernelArgs a, const Wor
 // ---- the latency lane (duo_kernel.cuh): which sets of a batch get two warps ------------------------------------------
 // Decided on the device from the sorted step counts, so the host never waits: the first n sets of the descending-work
 // queue get two warps each (queue [0, n), counter[5] / counter[4]) and the one-set-per-warp queue starts at n (counter[0]).  Both kernels give the same bits for a set, so n is free to follow the load:
-//   S > warps        the batch fills the GPU: only sets whose step count exceeds half the per-warp share of the whole batch
-//                    (they would still be running when everything else has finished), at most one per two SMs;
+//   S > warps        the batch fills the GPU: only sets whose step count exceeds 0.9 of the per-warp share of the whole batch
+//                    (they would still be running when everything else has finished), at most one per two SMs.  Measured
+//                    on shards of the 10^5-draw bench ensemble: longest set / share = 1.59 gains 12 %, 0.96 / 0.85 / 0.80 gain
+//                    nothing (profiles/r2_latency_lane_probe.jsonl); round 2's first threshold of 0.5 sent 74 sets of a uniform
+//                    two-sets-per-warp batch (2368 posterior rows at dr = 0.1) to the lane and cost it 25 % (356 -> 446 ms);
 //   warps/2 < S      every set has a warp to itself: the sets within 1.6x (the duo's gain) of the longest one, as far as the
 //                    registers they take from the other kernel allow (a duo CTA displaces a four-warp CTA);
 //   S <= warps/2     every set.
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(1024) duo_plan_kernel(long long S, const unsig
   double thr;
   long long cap;
   if (all) { thr = -1.0; cap = S; }
-  else if (S > warps) { thr = 0.5 * (double)s_total / (double)warps; cap = nsm / 2; }
+  else if (S > warps) { thr = 0.9 * (double)s_total / (double)warps; cap = nsm / 2; }
   else if (2 * S > warps) { thr = 0.625 * (double)keys[0]; cap = (warps - S) / 4; }
   else { thr = -1.0; cap = S; }
   const long long lim = S < cap ? S : cap;
@@ -972,6 +975,94 @@ int gab1_solve_batch(const gab1_opts* o, int64_t S, const double* Co, int64_t Co
   for (auto& t : th) t.join();
   for (int g = 0; g < nd; ++g)
     if (rcs[g]) return fail(rcs[g], "device %d: %s", devs[g], msgs[g].c_str());
+  return 0;
+}
+
+// ---- certified solve (gab1pde.h) ---------------------------------------------------------------------------------
+// The explicit scheme's dt ignores the second-order rate x concentration terms (basepdesolver.jl:30), so a few per mille of
+// wide prior draws sit at the edge of stability: an alternating mode amplifies last-bit differences by 1e5..1e13 over the
+// 4e4 steps without blowing up, and no arithmetic but the reference's own reproduces the reference there.  Those sets are
+// found by the response of the final state to a one-ulp change of the initial concentrations (two fast solves) and
+// re-solved with the strict kernels (arith = 1: bit-identical to the oracle), whose rows replace the fast ones.
+int gab1_solve_batch_certified(const gab1_opts* o, int64_t S, const double* Co, int64_t Co_stride, const double* D,
+                               const double* k, const double* dt, const double* r, double* out, int32_t* status,
+                               int32_t* n_saved, int64_t* n_steps, int64_t* n_bc_iters, double response, int32_t* resolved,
+                               int64_t* n_resolved) {
+  if (n_resolved) *n_resolved = 0;
+  if (int rc = check_opts(o)) return rc;
+  if (S < 0) return fail(-2, "S must be >= 0");
+  if (resolved) for (int64_t s = 0; s < S; ++s) resolved[s] = 0;
+  if (S == 0) return 0;
+  if (Co_stride != 0 && Co_stride != GAB1_N_CO) return fail(-2, "Co_stride must be 0 or 5");
+  if (!(response > 0.0)) response = 1e-12;
+  // the caller's solve; status and iteration counts are needed here whether or not the caller wants them
+  std::vector<int32_t> st_own, sv_own;
+  std::vector<int64_t> ns_own, bc_own;
+  if (!status) { st_own.resize(S); status = st_own.data(); }
+  if (!n_saved) { sv_own.resize(S); n_saved = sv_own.data(); }
+  if (!n_steps) { ns_own.resize(S); n_steps = ns_own.data(); }
+  if (!n_bc_iters) { bc_own.resize(S); n_bc_iters = bc_own.data(); }
+  if (int rc = gab1_solve_batch(o, S, Co, Co_stride, D, k, dt, r, out, status, n_saved, n_steps, n_bc_iters)) return rc;
+  if (o->arith == 1) return 0;                       // already the reference's arithmetic
+  // final states at Co and at Co moved one ulp up
+  gab1_opts fs = *o;
+  fs.out_mode = GAB1_OUT_FINAL_STATE;
+  const int64_t nf = gab1_out_doubles_per_set(&fs), nout = gab1_out_doubles_per_set(o);
+  const int64_t nco = Co_stride ? S * GAB1_N_CO : GAB1_N_CO;
+  std::vector<double> Co_up(nco), A, B((size_t)S * nf);
+  for (int64_t i = 0; i < nco; ++i) Co_up[i] = nextafter(Co[i], INFINITY);
+  std::vector<int32_t> sa_own, sb(S);
+  std::vector<int64_t> ba_own, bb(S);
+  const double* a = out;
+  const int32_t* sa = status;
+  const int64_t* ba = n_bc_iters;
+  if (o->out_mode != GAB1_OUT_FINAL_STATE) {
+    A.resize((size_t)S * nf); sa_own.resize(S); ba_own.resize(S);
+    if (int rc = gab1_solve_batch(&fs, S, Co, Co_stride, D, k, dt, r, A.data(), sa_own.data(), nullptr, nullptr, ba_own.data())) return rc;
+    a = A.data(); sa = sa_own.data(); ba = ba_own.data();
+  }
+  if (int rc = gab1_solve_batch(&fs, S, Co_up.data(), Co_stride, D, k, dt, r, B.data(), sb.data(), nullptr, nullptr, bb.data())) return rc;
+  std::vector<int64_t> idx;
+  for (int64_t s = 0; s < S; ++s) {
+    const double* as = a + s * nf;
+    const double* bs = B.data() + s * nf;
+    double scale = 0.0;
+    for (int64_t i = 0; i < nf; ++i) if (isfinite(as[i]) && fabs(as[i]) > scale) scale = fabs(as[i]);
+    double e = 0.0;
+    for (int64_t i = 0; i < nf; ++i) {
+      if (isnan(as[i]) != isnan(bs[i])) { e = INFINITY; break; }
+      if (!isfinite(as[i])) continue;
+      const double den = fmax(fabs(as[i]), 1e-6 * scale);
+      if (den > 0.0) { const double d = fabs(bs[i] - as[i]) / den; if (d > e || isnan(d)) e = isnan(d) ? INFINITY : d; }
+    }
+    const bool both_diverge = (sa[s] & GAB1_ST_NAN) && (sb[s] & GAB1_ST_NAN);     // NaN either way: dropped by every caller
+    if ((e >= response || ba[s] != bb[s] || sa[s] != sb[s]) && !both_diverge) idx.push_back(s);
+  }
+  if (n_resolved) *n_resolved = (int64_t)idx.size();
+  if (idx.empty()) return 0;
+  // strict re-solve of the flagged sets, gathered into a dense batch
+  const int64_t F = (int64_t)idx.size();
+  std::vector<double> Dg((size_t)F * GAB1_N_D), kg((size_t)F * GAB1_N_K), dtg(F), Cog(Co_stride ? (size_t)F * GAB1_N_CO : 0),
+      og((size_t)F * nout);
+  std::vector<int32_t> sg(F), svg(F);
+  std::vector<int64_t> nsg(F), bcg(F);
+  for (int64_t j = 0; j < F; ++j) {
+    const int64_t s = idx[j];
+    memcpy(&Dg[j * GAB1_N_D], D + s * GAB1_N_D, sizeof(double) * GAB1_N_D);
+    memcpy(&kg[j * GAB1_N_K], k + s * GAB1_N_K, sizeof(double) * GAB1_N_K);
+    dtg[j] = dt[s];
+    if (Co_stride) memcpy(&Cog[j * GAB1_N_CO], Co + s * GAB1_N_CO, sizeof(double) * GAB1_N_CO);
+  }
+  gab1_opts so = *o;
+  so.arith = 1;
+  if (int rc = gab1_solve_batch(&so, F, Co_stride ? Cog.data() : Co, Co_stride, Dg.data(), kg.data(), dtg.data(), r, og.data(),
+                                sg.data(), svg.data(), nsg.data(), bcg.data())) return rc;
+  for (int64_t j = 0; j < F; ++j) {
+    const int64_t s = idx[j];
+    memcpy(out + s * nout, &og[j * nout], sizeof(double) * nout);
+    status[s] = sg[j]; n_saved[s] = svg[j]; n_steps[s] = nsg[j]; n_bc_iters[s] = bcg[j];
+    if (resolved) resolved[s] = 1;
+  }
   return 0;
 }
 

@@ -62,13 +62,7 @@ __device__ __forceinline__ double gang_node(const double* state, int s, int q, i
 
 template <int G, int KN, typename F>
 __device__ __forceinline__ bool gang_write_row(double* dst, int P, int lane, F val) {
-  bool nan_seen = false;
-  for (int n = lane; n < P; n += 32) {
-    const double v = val(n);
-    nan_seen |= isnan(v);
-    dst[n] = v;
-  }
-  return __any_sync(FULL, nan_seen);
+  return store_row_v2(dst, P, lane, val);     // 16-byte stores (solver_kernel.cuh)
 }
 
 template <int G, int KN>

@@ -72,9 +72,7 @@ __device__ __forceinline__ double2 lds2(unsigned addr) {
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
   return v;
 }
-__device__ __forceinline__ void sts2(unsigned addr, double x, double y) {
-  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
-}
+// sts2: solver_kernel.cuh
 
 // ---------------------------------------------------------------------------------------------------------------
 // Interior token.  A scheduler holds two of these warps (255 registers each).  Left alone they drift into phase:

@@ -33,11 +33,23 @@ enum { mE, mES, mESmES, E, EG2, EG2G1, EG2PG1, EG2PG1S, NMB };                  
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int WS_HDR = 32;          // per-warp smem header: [0,16) interior-neighbour stage, [16,32) boundary stage
 constexpr int ML = 10;              // first membrane lane
-// Halo exchange area of the fast one-set-per-warp kernel with K >= 4 nodes per lane: the interior halo crosses lanes
-// through shared memory (20 STS.64 + 20 LDS.64 per step) instead of 40 32-bit shuffles plus the register moves that
-// re-pair their halves.  Measured on B200: K = 4 (dr = 0.1) 378.9 vs 388.9 ms; K = 2 (dr = 0.2) 126.8 vs 117.2 ms — with
-// two nodes per lane there is too little independent work to cover store -> warp barrier -> load, so K <= 2 keeps shuffles.
-constexpr int WS_EX = 2 * 10 * 32;  // doubles per warp: [species][lane] of the last node, then of the first node
+// Halo exchange area of the fast one-set-per-warp kernel with K >= 4 nodes per lane: the interior halo crosses lanes through
+// shared memory instead of 40 32-bit shuffles plus the ~27 register moves that re-pair their halves.
+// Pipelined form (GAB1_HALO_PIPE, round 2): a lane stores the two edge nodes of its run right after the interior update —
+// behind the warp barrier that already separates interior and fixed point, i.e. inside the latency-bound membrane block —
+// and loads its neighbours' edges at the top of the NEXT step, so neither the stores nor a barrier sit in front of the loads:
+// 10 + 10 128-bit accesses per step.  The three old-time membrane values a lane needs at the top of a step (x[lane + 1],
+// x[src_den], x[src_num]) and the boundary values come the same way.  Measured on B200 (2368 posterior rows, final state):
+//   K = 4 (dr = 0.1)  shuffles 388.9 ms, store -> barrier -> load at the top of the step (round 1) 378.9 ms, pipelined 356.4 ms;
+//   K = 2 (dr = 0.2)  shuffles 116.2 ms / 408.6 ms (5000 rows / 20 000 prior draws), unpipelined 126.8 ms, pipelined 122.9 ms /
+//                     432.7 ms although it issues 12 % fewer instructions per step (278 against 317): it moves every halo value
+//                     through the shared-memory data pipe twice (store + load; a shuffle moves it once) and takes that pipe
+//                     from 46 % to ~75 % busy at two nodes per lane — so K <= 2 keeps the shuffles.
+constexpr int WS_EX = 2 * 10 * 32 + 32;  // doubles per warp: [species pair][lane][2] of the last slot, the same of the first slot, then x[lane]
+#ifndef GAB1_HALO_PIPE
+#define GAB1_HALO_PIPE 1
+#endif
+constexpr int WS_EX_X = 2 * 10 * 32;    // offset of x[lane] inside the exchange area
 
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -75,6 +87,12 @@ __device__ __forceinline__ double lds(unsigned addr) {
 }
 __device__ __forceinline__ void sts(unsigned addr, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void lds2(unsigned addr, double& v0, double& v1) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sts2(unsigned addr, double v0, double v1) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v0), "d"(v1) : "memory");
 }
 __device__ __forceinline__ bool is_special(double x) {   // zero, Inf or NaN — decided on the bit pattern, off the FP64 pipe
   const unsigned hi = (unsigned)__double2hiint(x) & 0x7fffffffu;
@@ -114,15 +132,34 @@ __device__ __forceinline__ void stage_row(double* row, int lane, const Grid<K>& 
   }
   __syncwarp();
 }
-__device__ __forceinline__ bool flush_row(double* dst, const double* row, int P, int lane) {
+// 16-byte stores: a lane writes two consecutive nodes with one st.global.v2.f64 (a 51-node column is 26 lanes' worth instead of
+// two passes of 8-byte stores); a column that starts on an odd double (every other one when P is odd) sheds its first node
+// as a scalar so that the pairs are aligned.  The same code serves device memory and mapped host memory.
+__device__ __forceinline__ void stg2(double* p, double v0, double v1) {
+  asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v0), "d"(v1) : "memory");
+}
+template <typename F>
+__device__ __forceinline__ bool store_row_v2(double* dst, int P, int lane, F val) {
   bool nan_seen = false;
-  for (int n = lane; n < P; n += 32) {
-    const double v = row[n];
-    nan_seen |= isnan(v);
-    dst[n] = v;
+  const int head = (int)((reinterpret_cast<unsigned long long>(dst) >> 3) & 1ull);
+  const int npairs = (P - head) >> 1;
+  for (int j = lane; j < npairs; j += 32) {
+    const int n = head + 2 * j;
+    const double v0 = val(n), v1 = val(n + 1);
+    nan_seen |= isnan(v0) || isnan(v1);
+    stg2(dst + n, v0, v1);
   }
-  __syncwarp();
+  if (lane == 31) {
+    if (head) { const double v = val(0); nan_seen |= isnan(v); dst[0] = v; }
+    const int tail = head + 2 * npairs;
+    if (tail < P) { const double v = val(tail); nan_seen |= isnan(v); dst[tail] = v; }
+  }
   return __any_sync(FULL, nan_seen);
+}
+__device__ __forceinline__ bool flush_row(double* dst, const double* row, int P, int lane) {
+  const bool nan_seen = store_row_v2(dst, P, lane, [&](int n) { return row[n]; });
+  __syncwarp();
+  return nan_seen;
 }
 
 template <int K>
@@ -636,6 +673,27 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
     // x: the value this lane tracks across iterations and steps — boundary value u[Nr+1] of species `lane`
     // (lanes 0..9), membrane species lane-10 (lanes 10..17), Etot (lane 18), zero elsewhere
     double x = (lane == ML + mE) ? CoEGFR : 0.0;
+    // ---- exchange area (pipelined halo, see WS_EX): [pair p][lane][2] of the last slot, the same of the first slot, x[lane] ----
+    constexpr bool PIPE = GAB1_HALO_PIPE && K >= 4;
+    const unsigned ex = ws_s + 8u * (unsigned)(WS_HDR + 2 * a.P_pad);
+    const unsigned ex_own = ex + 16u * (unsigned)lane;
+    const unsigned ex_l = ex + 16u * (unsigned)(lane > 0 ? lane - 1 : 0);                       // last slot of the lane to the left
+    const unsigned ex_r = ex + 16u * (unsigned)(NCY / 2 * 32 + (lane < 31 ? lane + 1 : 31));    // first slot of the lane to the right
+    const unsigned xa = ex + 8u * (unsigned)WS_EX_X;
+    // where this lane's x goes at the end of a step: a closure lane writes the new boundary value straight into lane_b's
+    // last-slot entry (every lane then reloads its last slot from its own entry: unpredicated 128-bit loads into the state
+    // registers, and the halo entry of lane_b holds the boundary node); the other lanes write x[lane]
+    const unsigned x_st = lane < NCY ? ex + 16u * (unsigned)((lane >> 1) * 32 + lane_b) + 8u * (unsigned)(lane & 1) : xa + 8u * (unsigned)lane;
+    if constexpr (PIPE) {
+      __syncwarp();
+#pragma unroll
+      for (int p = 0; p < NCY / 2; ++p) {
+        sts2(ex_own + 512u * p, u[2 * p][K - 1], u[2 * p + 1][K - 1]);
+        sts2(ex_own + 512u * (NCY / 2 + p), u[2 * p][0], u[2 * p + 1][0]);
+      }
+      sts(xa + 8u * (unsigned)lane, x);
+      __syncwarp();
+    }
 
     // ---- time loop.  Every rare event (snapshot due, pulse-chase switch, last step, dead state) hides behind one integer
     //      countdown, so the common step carries a single predictable branch besides the fixed-point loop.  `plan`
@@ -664,12 +722,13 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
       // ---- membrane block prologue: everything that depends only on old-time values.  It is independent of the
       //      interior update below, so the two instruction streams interleave and hide each other's latency ----
       const double m_old = x;                                        // lanes >= 10: value at the old time level
-      const double m_next = shfl_down1(m_old);
+      const double m_next = PIPE ? lds(xa + 8u * (unsigned)(lane < 31 ? lane + 1 : 31)) : shfl_down1(m_old);
       const double f = fma(m_old, fma(alpha2, m_old, alpha), -(beta * m_next));
       const double base = fma(dt, fma(s_own, f, s_src * shfl(f, f_src)), m_old);
       // the first iterate of the membrane column is the old-time column, so these two shuffles serve both the
       // old-time flux coefficients and the first pass of the fixed point
-      const double Md1 = shfl(m_old, src_den), Mn1 = shfl(m_old, src_num);
+      const double Md1 = PIPE ? lds(xa + 8u * (unsigned)src_den) : shfl(m_old, src_den);
+      const double Mn1 = PIPE ? lds(xa + 8u * (unsigned)src_num) : shfl(m_old, src_num);
       const double A_t = kf_t * Md1;                                 // F = dt*(kf*M_den*b - kr*M_num), old-time M
       const double B_t = kr_t * Mn1;
       const double rden1 = fast_recip(fma(cf, Md1, 1.0));            // 1/(1 + cf*M_den) of the first pass
@@ -677,8 +736,13 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
       // ---- interior: D*lap + kinetics, explicit Euler, updated in place (basepdesolver.jl:150-180) ----
       {
         double hl[NCY], hr[NCY];
-        if constexpr (K >= 4) {
-          const unsigned ex = ws_s + 8u * (unsigned)(WS_HDR + 2 * a.P_pad);
+        if constexpr (PIPE) {
+#pragma unroll
+          for (int p = 0; p < NCY / 2; ++p) {
+            lds2(ex_l + 512u * p, hl[2 * p], hl[2 * p + 1]);
+            lds2(ex_r + 512u * p, hr[2 * p], hr[2 * p + 1]);
+          }
+        } else if constexpr (K >= 4) {
 #pragma unroll
           for (int q = 0; q < NCY; ++q) {
             sts(ex + 8u * (unsigned)(q * 32 + lane), u[q][K - 1]);
@@ -748,6 +812,15 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
       const double Iq = lds(ws_s + 8 * iq_idx);
       // aSFK: I_a + ca*Etot*I_i/(1 + cf*Etot) = (I_a + (cf*I_a + ca*I_i)*Etot)/(1 + cf*Etot)   (basepdesolver.jl:206-207)
       const double cr = lane == aSFK ? fma(cf, Iq, ca * lds(ws_s + 8 * iSFK)) : cr_fixed;
+      if constexpr (PIPE) {
+        // this step's edge nodes for the neighbours' next step: every lane has finished reading the old ones (the barrier
+        // above), and the barrier below the fixed point separates these stores from the loads at the top of the next step
+#pragma unroll
+        for (int p = 0; p < NCY / 2; ++p) {
+          if (lane != lane_b) sts2(ex_own + 512u * p, u[2 * p][K - 1], u[2 * p + 1][K - 1]);
+          sts2(ex_own + 512u * (NCY / 2 + p), u[2 * p][0], u[2 * p + 1][0]);
+        }
+      }
 
       // ---- fixed-point iterations (basepdesolver.jl:197-242); the first pass is peeled: its reciprocal is ready ----
       int it = 1;               // the host routes `maxiters = 0` to the strict kernel: at least one pass runs here
@@ -791,11 +864,18 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
       }
       bc_total += it;
       // ---- boundary values back to the lane that owns node Nr ----
-      if (lane < NCY) sts(ws_s + 8 * (16 + lane), x);
-      __syncwarp();
-      if (lane == lane_b) {
+      if constexpr (PIPE) {
+        sts(x_st, x);
+        __syncwarp();
 #pragma unroll
-        for (int q = 0; q < NCY; ++q) u[q][idx_b] = lds(ws_s + 8 * (16 + q));
+        for (int p = 0; p < NCY / 2; ++p) lds2(ex_own + 512u * p, u[2 * p][K - 1], u[2 * p + 1][K - 1]);
+      } else {
+        if (lane < NCY) sts(ws_s + 8 * (16 + lane), x);
+        __syncwarp();
+        if (lane == lane_b) {
+#pragma unroll
+          for (int q = 0; q < NCY; ++q) u[q][idx_b] = lds(ws_s + 8 * (16 + q));
+        }
       }
       if (unconverged || nan_exit) {
         bool all_nan = (lane < ML || lane >= LE) || isnan(x);
@@ -912,7 +992,7 @@ template <int K, int MODE>
 __global__ void __launch_bounds__(32 * GAB1_WARPS, (MODE == MODE_STRICT || K > 2) ? 1 : GAB1_MINB)
 solve_kernel(const KernelArgs a) {
   if (a.guard && *a.guard != a.guard_expect) return;
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* ws = smem + (size_t)warp * (WS_HDR + 2 * a.P_pad + WS_EX);
   const int Nr = a.o.Nr;

@@ -203,9 +203,14 @@ team_kernel(const KernelArgs a) {
       bool ns = false;
       for (int mi = 0; mi < 12; ++mi) {
         if (!((a.o.matrix_mask >> mi) & 1u)) continue;
-        for (int n = tid; n < P; n += T) {
-          const double v = mi < 10 ? at_node(b, kSpecies[mi], n) : (mi == GAB1_M_PG1tot ? ptot_at(b, n) : stot_at(b, n));
-          oset[o2 + (long long)c * P + n] = v;
+        // 16-byte stores, pairs aligned by shedding the first node of a column that starts on an odd double (solver_kernel.cuh: store_row_v2)
+        auto val = [&](int n) { return mi < 10 ? at_node(b, kSpecies[mi], n) : (mi == GAB1_M_PG1tot ? ptot_at(b, n) : stot_at(b, n)); };
+        double* col = oset + o2 + (long long)c * P;
+        const int head = (int)((reinterpret_cast<unsigned long long>(col) >> 3) & 1ull), npairs = (P - head) >> 1;
+        for (int j = tid; j < npairs; j += T) stg2(col + head + 2 * j, val(head + 2 * j), val(head + 2 * j + 1));
+        if (tid == T - 1) {
+          if (head) col[0] = val(0);
+          if (head + 2 * npairs < P) col[P - 1] = val(P - 1);
         }
         o2 += (long long)P * Cn;
       }

@@ -159,6 +159,11 @@ class Frontend:
         Dmat = np.ascontiguousarray(Dmat, dtype=np.float64).reshape(-1, abi.N_D)
         kmat = np.ascontiguousarray(kmat, dtype=np.float64).reshape(-1, abi.N_K)
         dtv = params.default_dt(Dmat, kmat, dr) if dt is None else np.broadcast_to(np.asarray(dt, float), (Dmat.shape[0],)).copy()
+        if certify and hasattr(self.backend, "solve_certified"):       # the C ABI's own entry point (gab1_solve_batch_certified)
+            out, status, n_saved, n_steps, n_bc, idx = self.backend.solve_certified(o, Co, Dmat, kmat, dtv, r, self.CERTIFY_RESPONSE)
+            res = BatchResult(o, out, status, n_saved, n_steps, n_bc, r, dtv)
+            res.resolved_strict = idx
+            return res
         out, status, n_saved, n_steps, n_bc = self.backend.solve(o, Co, Dmat, kmat, dtv, r)
         res = BatchResult(o, out, status, n_saved, n_steps, n_bc, r, dtv)
         if certify and hasattr(self.backend, "strict_twin"):
@@ -170,7 +175,9 @@ class Frontend:
     CERTIFY_RESPONSE = 1e-12
 
     def _certify(self, res: BatchResult, Co, Dmat, kmat) -> None:
-        """Makes the 1e-9 contract hold for EVERY non-diverging set, ill-conditioned ones included (opt-in, ~2.3x the cost).
+        """Python restatement of gab1_solve_batch_certified (the C ABI entry point `certify=True` uses; this one is kept as
+        its cross-check, tests/test_gpu_census.py).
+        Makes the 1e-9 contract hold for EVERY non-diverging set, ill-conditioned ones included (opt-in, ~2.3x the cost).
 
         The explicit scheme's time step ignores the second-order rate x concentration terms (basepdesolver.jl:30), so a few
         per mille of wide prior draws sit at the edge of stability: an alternating mode amplifies last-bit differences by

@@ -98,8 +98,20 @@ def test_census_config2_synthetic_priors(pkg, gfe, ofe):
     live_ill = set(np.flatnonzero(ill & ((ref.status & 1) == 0)).tolist())
     assert live_ill <= set(rep_c["resolved_strict"]), (live_ill, rep_c["resolved_strict"])
     assert len(cert.resolved_strict) <= 60, "the certification should re-solve a few per cent of the draws at most"
+    # certify=True runs the C ABI's gab1_solve_batch_certified; the Python restatement of the same procedure agrees with it
+    py = gfe.sapdesolver_batch(Co, ens[:, :7], ens[:, 7:], out_mode=pkg.abi.OUT_FINAL_STATE, **kw)
+    gfe._certify(py, Co, ens[:, :7], ens[:, 7:])
+    np.testing.assert_array_equal(py.resolved_strict, cert.resolved_strict)
+    assert ((py.out.view(np.uint64) == cert.out.view(np.uint64)) | (np.isnan(py.out) & np.isnan(cert.out))).all()
+    np.testing.assert_array_equal(py.n_bc_iters, cert.n_bc_iters)
+    # ... and with another output mode (the final states are then solved on the side): the re-solved rows are the oracle's bits
+    six_c = gfe.sapdesolver_batch(Co, ens[:, :7], ens[:, 7:], out_mode=pkg.abi.OUT_SIX, certify=True, **kw)
+    np.testing.assert_array_equal(six_c.resolved_strict, cert.resolved_strict)
     six = gfe.sapdesolver_batch(Co, ens[:, :7], ens[:, 7:], out_mode=pkg.abi.OUT_SIX, **kw)
     six_ref = ofe.sapdesolver_batch(Co, ens[:, :7], ens[:, 7:], out_mode=pkg.abi.OUT_SIX, **kw)
+    rs = cert.resolved_strict
+    assert ((six_c.out[rs].view(np.uint64) == six_ref.out[rs].view(np.uint64)) | (np.isnan(six_c.out[rs]) & np.isnan(six_ref.out[rs]))).all()
+    np.testing.assert_array_equal(six_c.status[rs], six_ref.status[rs])
     np.testing.assert_array_equal(six.status[~ill], six_ref.status[~ill])
     sel = ~ill & ((ref.status & 1) == 0)
     np.testing.assert_array_equal(six.n_bc_iters[sel], six_ref.n_bc_iters[sel])
