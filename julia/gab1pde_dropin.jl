@@ -82,10 +82,13 @@ end
 struct Batch
     o::Opts; out::Matrix{Float64}; status::Vector{Int32}; n_saved::Vector{Int32}
     n_steps::Vector{Int64}; n_bc_iters::Vector{Int64}; r::Vector{Float64}; dt::Vector{Float64}
+    resolved_strict::Vector{Int}       # certify=true: the sets (1-based) that were re-solved with the strict kernels
 end
 
-"Run S parameter sets (rows of Dmat S×7 and kmat S×17). Co is a 5-vector shared by all sets or S×5."
-function solve(o::Opts, Co, Dmat, kmat, dt::Vector{Float64}, r::Vector{Float64})
+"Run S parameter sets (rows of Dmat S×7 and kmat S×17). Co is a 5-vector shared by all sets or S×5.
+certify=true goes through gab1_solve_batch_certified: every set whose final state responds to a one-ulp change of Co (two
+extra fast solves) is re-solved with the strict kernels, so that the 1e-9 contract holds for ill-conditioned sets too."
+function solve(o::Opts, Co, Dmat, kmat, dt::Vector{Float64}, r::Vector{Float64}; certify::Bool=false)
     S = size(Dmat, 1)
     length(r) == o.Nr + 1 || throw(BoundsError(r, o.Nr + 1))           # the reference indexes r[Nr+1]
     Dt = permutedims(Float64.(Dmat)); kt = permutedims(Float64.(kmat))   # row-major for C
@@ -93,12 +96,21 @@ function solve(o::Opts, Co, Dmat, kmat, dt::Vector{Float64}, r::Vector{Float64})
     n = out_doubles(o)
     out = result_matrix(n, S); status = zeros(Int32, S); n_saved = zeros(Int32, S)
     n_steps = zeros(Int64, S); n_bc = zeros(Int64, S)
+    if certify
+        resolved = zeros(Int32, S); n_res = Ref{Int64}(0)
+        rc = ccall((:gab1_solve_batch_certified, LIB), Cint,
+                   (Ref{Opts}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                    Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}, Float64, Ptr{Int32}, Ref{Int64}),
+                   o, S, Cot, stride, Dt, kt, dt, r, out, status, n_saved, n_steps, n_bc, 0.0, resolved, n_res)
+        rc == 0 || error("gab1_solve_batch_certified: " * last_error())
+        return Batch(o, out, status, n_saved, n_steps, n_bc, r, dt, findall(!=(0), resolved))
+    end
     rc = ccall((:gab1_solve_batch, LIB), Cint,
                (Ref{Opts}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
                 Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}),
                o, S, Cot, stride, Dt, kt, dt, r, out, status, n_saved, n_steps, n_bc)
     rc == 0 || error("gab1_solve_batch: " * last_error())
-    Batch(o, out, status, n_saved, n_steps, n_bc, r, dt)
+    Batch(o, out, status, n_saved, n_steps, n_bc, r, dt, Int[])
 end
 
 function matrix(b::Batch, name::Symbol, j::Int)
@@ -122,20 +134,20 @@ f64(x, what) = eltype(x) <: AbstractFloat || eltype(x) <: Integer ? Float64.(x) 
 "Batched sibling of `pdesolver` (basepdesolver.jl:25-312): one row of Dmat / kmat per parameter set."
 function pdesolver_batch(Co, Dmat, kmat; R=10.0, dr=0.1, tf=5.0, Nts=100,
                          dt=[default_dt(Dmat[j, :], kmat[j, :], dr) for j in axes(Dmat, 1)],
-                         dt_save=tf / Nts, maxiters=100, tol=1.0e-6, r=collect(0.0:dr:R), kw...)
-    solve(make_opts(; R, dr, tf, Nts, dt_save, maxiters, tol, kw...), Co, Dmat, kmat, Float64.(dt), r)
+                         dt_save=tf / Nts, maxiters=100, tol=1.0e-6, r=collect(0.0:dr:R), certify=false, kw...)
+    solve(make_opts(; R, dr, tf, Nts, dt_save, maxiters, tol, kw...), Co, Dmat, kmat, Float64.(dt), r; certify)
 end
 
 "Batched sibling of `sapdesolver` / `sapdesolver_membSFK` (sapdesolver.jl:55-280, sapdesolver_memb-SFK.jl:55-281)."
 function sapdesolver_batch(Co, Dmat, kmat; R=10.0, dr=0.2, tf=5.0,
                            dt=[default_dt(Dmat[j, :], kmat[j, :], dr) for j in axes(Dmat, 1)],
                            maxiters=20, tol=1.0e-3, membSFK=false, out_mode=OUT_FINAL4, r=collect(0.0:dr:R),
-                           iter_cap=ITER_CAP[])
+                           iter_cap=ITER_CAP[], certify=false)
     # membSFK: the reference's `while error > tol` has no cap (sapdesolver_memb-SFK.jl:177) and spins forever on a fixed
     # point that never meets tol; the library stops such a step after `iter_cap` passes and flags the set (ST_ITER_CAP)
     o = make_opts(; R, dr, tf, Nts=1, maxiters=membSFK ? iter_cap : maxiters, tol, out_mode,
                   sfk_mode=membSFK ? 1 : 0, bc_loop=membSFK ? 1 : 0, pg1tot_form=membSFK ? 1 : 0)
-    solve(o, Co, Dmat, kmat, Float64.(dt), r)
+    solve(o, Co, Dmat, kmat, Float64.(dt), r; certify)
 end
 
 function sol_tuple(b::Batch, j; extra=false, ncol=b.o.Nts + 1)
