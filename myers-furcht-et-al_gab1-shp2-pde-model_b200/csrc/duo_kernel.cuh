@@ -563,6 +563,7 @@ __device__ void duo_solve_set(const KernelArgs& a, long long set, int lane, bool
 template <int K, int MODE>
 __global__ void __launch_bounds__(128, 2)
 duo_solve_kernel(const KernelArgs a) {
+  if (a.guard && *a.guard != a.guard_expect) return;      // the plan sent nothing to the latency lane: solve_kernel runs instead
   extern __shared__ __align__(16) double smem[];
   __shared__ unsigned s_item[2];
   __shared__ int s_flags[2][2];       // per pair: [0] the state is all NaN, [1] warp B's status bits

@@ -152,7 +152,7 @@ constexpr size_t kCounterBytes = 8192;   // 64 queue words + 4 reservation words
 size_t carve(Workspace& w, void* base, long long S) {
   size_t off = 0;
   auto take = [&](size_t bytes) { void* p = base ? (char*)base + off : nullptr; off += align_up(bytes, 256); return p; };
-  w.counter = (unsigned*)take(kCounterBytes);     // [0] queue head, [1] guard word, [2..5] hand-over / latency lane, [64..] SM reservations
+  w.counter = (unsigned*)take(kCounterBytes);     // [0] queue head, [1] guard word, [2..9] hand-over / latency lane, [10] fused-or-plain guard, [64..] SM reservations
   w.keys_in = (unsigned*)take(sizeof(unsigned) * (size_t)S);
   w.keys_out = (unsigned*)take(sizeof(unsigned) * (size_t)S);
   w.vals_in = (int*)take(sizeof(int) * (size_t)S);
@@ -221,10 +221,14 @@ __global__ void __launch_bounds__(1024) duo_plan_kernel(long long S, const unsig
   for (long long i = tid; i < lim; i += 1024) local += ((double)keys[i] > thr) ? 1u : 0u;
   if (local) atomicAdd(&s_cnt, local);
   __syncthreads();
-  if (tid == 0) { counter[0] = s_cnt; counter[4] = s_cnt; counter[5] = 0u; }
+  if (tid == 0) { counter[0] = s_cnt; counter[4] = s_cnt; counter[5] = 0u; counter[10] = s_cnt ? 1u : 0u; }
 }
 
-// The plan, then ONE launch: the one-set-per-warp kernel with the latency lane in front (duo_kernel.cuh: duo_solve_kernel).
+// The plan, then the one-set-per-warp kernel with the latency lane in front (duo_kernel.cuh: duo_solve_kernel) — and, behind a
+// guard word the plan writes, the plain one-set-per-warp kernel: exactly one of the two runs (the other's CTAs return at
+// once).  The fused kernel's throughput lane carries 13 more register moves per step than solve_kernel (ptxas allocates
+// for both lanes: 422 against 409 instructions, 120.5 vs 116.3 ms on 4736 posterior rows), so a batch that sends
+// nothing to the latency lane — every full batch without a heavy tail — should not pay for it.
 int solve_with_duo(int K, int mode, gab1::KernelArgs a, const Workspace& w, int device, cudaStream_t stream, bool all) {
   int nsm = 148;
   CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
@@ -240,7 +244,13 @@ int solve_with_duo(int K, int mode, gab1::KernelArgs a, const Workspace& w, int 
   if (const char* e = getenv("GAB1_ISOLATE")) {
     if (a.isolate) a.isolate = strcmp(e, "sched") == 0 ? 2 : (strcmp(e, "sm") == 0 ? 1 : (e[0] == '0' ? 0 : a.isolate));
   }
-  return gab1::launch_duo_kernel(K, mode, a, device, stream);
+  a.guard = (const int*)(w.counter + 10);     // written by the plan: 1 = the latency lane has sets
+  a.guard_expect = 1;
+  if (int rc = gab1::launch_duo_kernel(K, mode, a, device, stream)) return rc;
+  if (all) return 0;
+  a.guard_expect = 0;                 // no set for the latency lane: the plain kernel, its queue starting at counter[0] = 0
+  a.dyn_count = nullptr; a.duo_counter = nullptr; a.sm_resv = nullptr; a.isolate = 0;
+  return gab1::launch_single_kernel(K, mode, a, device, stream);
 }
 
 int solve_device(const gab1_opts* o, int device, cudaStream_t stream, long long S, const double* Co, long long Co_stride,

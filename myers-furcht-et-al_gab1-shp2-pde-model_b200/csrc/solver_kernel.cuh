@@ -33,23 +33,19 @@ enum { mE, mES, mESmES, E, EG2, EG2G1, EG2PG1, EG2PG1S, NMB };                  
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int WS_HDR = 32;          // per-warp smem header: [0,16) interior-neighbour stage, [16,32) boundary stage
 constexpr int ML = 10;              // first membrane lane
-// Halo exchange area of the fast one-set-per-warp kernel with K >= 4 nodes per lane: the interior halo crosses lanes through
-// shared memory instead of 40 32-bit shuffles plus the ~27 register moves that re-pair their halves.
-// Pipelined form (GAB1_HALO_PIPE, round 2): a lane stores the two edge nodes of its run right after the interior update —
-// behind the warp barrier that already separates interior and fixed point, i.e. inside the latency-bound membrane block —
-// and loads its neighbours' edges at the top of the NEXT step, so neither the stores nor a barrier sit in front of the loads:
-// 10 + 10 128-bit accesses per step.  The three old-time membrane values a lane needs at the top of a step (x[lane + 1],
-// x[src_den], x[src_num]) and the boundary values come the same way.  Measured on B200 (2368 posterior rows, final state):
-//   K = 4 (dr = 0.1)  shuffles 388.9 ms, store -> barrier -> load at the top of the step (round 1) 378.9 ms, pipelined 356.4 ms;
-//   K = 2 (dr = 0.2)  shuffles 116.2 ms / 408.6 ms (5000 rows / 20 000 prior draws), unpipelined 126.8 ms, pipelined 122.9 ms /
-//                     432.7 ms although it issues 12 % fewer instructions per step (278 against 317): it moves every halo value
-//                     through the shared-memory data pipe twice (store + load; a shuffle moves it once) and takes that pipe
-//                     from 46 % to ~75 % busy at two nodes per lane — so K <= 2 keeps the shuffles.
-constexpr int WS_EX = 2 * 10 * 32 + 32;  // doubles per warp: [species pair][lane][2] of the last slot, the same of the first slot, then x[lane]
-#ifndef GAB1_HALO_PIPE
-#define GAB1_HALO_PIPE 1
-#endif
-constexpr int WS_EX_X = 2 * 10 * 32;    // offset of x[lane] inside the exchange area
+// Halo exchange area of the fast one-set-per-warp kernel with K >= 4 nodes per lane: the interior halo crosses lanes
+// through shared memory (20 STS.64 + 20 LDS.64 per step) instead of 40 32-bit shuffles plus the register moves that
+// re-pair their halves.  Measured on B200: K = 4 (dr = 0.1) 378.9 vs 388.9 ms; K = 2 (dr = 0.2) 126.8 vs 117.2 ms — with
+// two nodes per lane there is too little independent work to cover store -> warp barrier -> load, so K <= 2 keeps shuffles.
+// Round 2 tried the software-pipelined form (edge nodes stored behind the interior's barrier, i.e. inside the membrane block,
+// and loaded at the top of the NEXT step with 128-bit accesses; boundary values and the old-time membrane values likewise):
+// 12 % fewer instructions per step at K = 2 (278 against 317) and yet slower, 122.9 vs 116.2 ms / 432.7 vs 408.6 ms (5000
+// rows / 20 000 prior draws): every halo value crosses the shared-memory data pipe twice (store + load; a shuffle moves it
+// once), which takes that pipe from 46 % to ~75 % busy.  At K = 4 it measured equal to the form below (355.5 ms both, same
+// session) — so it was removed again (profiles/r2x_halo_pipe_timings.txt, r2y_ab_*.txt).  Serving only the three old-time
+// membrane values of the prologue from a shared x[lane] block (3 LDS.64 for 6 SHFL) does not pay either: ptxas answers with
+// more moves than the shuffles had (413 against 409 instructions in the loop).
+constexpr int WS_EX = 2 * 10 * 32;  // doubles per warp: [species][lane] of the last node, then of the first node
 
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -673,27 +669,6 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
     // x: the value this lane tracks across iterations and steps — boundary value u[Nr+1] of species `lane`
     // (lanes 0..9), membrane species lane-10 (lanes 10..17), Etot (lane 18), zero elsewhere
     double x = (lane == ML + mE) ? CoEGFR : 0.0;
-    // ---- exchange area (pipelined halo, see WS_EX): [pair p][lane][2] of the last slot, the same of the first slot, x[lane] ----
-    constexpr bool PIPE = GAB1_HALO_PIPE && K >= 4;
-    const unsigned ex = ws_s + 8u * (unsigned)(WS_HDR + 2 * a.P_pad);
-    const unsigned ex_own = ex + 16u * (unsigned)lane;
-    const unsigned ex_l = ex + 16u * (unsigned)(lane > 0 ? lane - 1 : 0);                       // last slot of the lane to the left
-    const unsigned ex_r = ex + 16u * (unsigned)(NCY / 2 * 32 + (lane < 31 ? lane + 1 : 31));    // first slot of the lane to the right
-    const unsigned xa = ex + 8u * (unsigned)WS_EX_X;
-    // where this lane's x goes at the end of a step: a closure lane writes the new boundary value straight into lane_b's
-    // last-slot entry (every lane then reloads its last slot from its own entry: unpredicated 128-bit loads into the state
-    // registers, and the halo entry of lane_b holds the boundary node); the other lanes write x[lane]
-    const unsigned x_st = lane < NCY ? ex + 16u * (unsigned)((lane >> 1) * 32 + lane_b) + 8u * (unsigned)(lane & 1) : xa + 8u * (unsigned)lane;
-    if constexpr (PIPE) {
-      __syncwarp();
-#pragma unroll
-      for (int p = 0; p < NCY / 2; ++p) {
-        sts2(ex_own + 512u * p, u[2 * p][K - 1], u[2 * p + 1][K - 1]);
-        sts2(ex_own + 512u * (NCY / 2 + p), u[2 * p][0], u[2 * p + 1][0]);
-      }
-      sts(xa + 8u * (unsigned)lane, x);
-      __syncwarp();
-    }
 
     // ---- time loop.  Every rare event (snapshot due, pulse-chase switch, last step, dead state) hides behind one integer
     //      countdown, so the common step carries a single predictable branch besides the fixed-point loop.  `plan`
@@ -722,13 +697,12 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
       // ---- membrane block prologue: everything that depends only on old-time values.  It is independent of the
       //      interior update below, so the two instruction streams interleave and hide each other's latency ----
       const double m_old = x;                                        // lanes >= 10: value at the old time level
-      const double m_next = PIPE ? lds(xa + 8u * (unsigned)(lane < 31 ? lane + 1 : 31)) : shfl_down1(m_old);
+      const double m_next = shfl_down1(m_old);
       const double f = fma(m_old, fma(alpha2, m_old, alpha), -(beta * m_next));
       const double base = fma(dt, fma(s_own, f, s_src * shfl(f, f_src)), m_old);
       // the first iterate of the membrane column is the old-time column, so these two shuffles serve both the
       // old-time flux coefficients and the first pass of the fixed point
-      const double Md1 = PIPE ? lds(xa + 8u * (unsigned)src_den) : shfl(m_old, src_den);
-      const double Mn1 = PIPE ? lds(xa + 8u * (unsigned)src_num) : shfl(m_old, src_num);
+      const double Md1 = shfl(m_old, src_den), Mn1 = shfl(m_old, src_num);
       const double A_t = kf_t * Md1;                                 // F = dt*(kf*M_den*b - kr*M_num), old-time M
       const double B_t = kr_t * Mn1;
       const double rden1 = fast_recip(fma(cf, Md1, 1.0));            // 1/(1 + cf*M_den) of the first pass
@@ -736,13 +710,8 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
       // ---- interior: D*lap + kinetics, explicit Euler, updated in place (basepdesolver.jl:150-180) ----
       {
         double hl[NCY], hr[NCY];
-        if constexpr (PIPE) {
-#pragma unroll
-          for (int p = 0; p < NCY / 2; ++p) {
-            lds2(ex_l + 512u * p, hl[2 * p], hl[2 * p + 1]);
-            lds2(ex_r + 512u * p, hr[2 * p], hr[2 * p + 1]);
-          }
-        } else if constexpr (K >= 4) {
+        if constexpr (K >= 4) {
+          const unsigned ex = ws_s + 8u * (unsigned)(WS_HDR + 2 * a.P_pad);
 #pragma unroll
           for (int q = 0; q < NCY; ++q) {
             sts(ex + 8u * (unsigned)(q * 32 + lane), u[q][K - 1]);
@@ -812,15 +781,6 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
       const double Iq = lds(ws_s + 8 * iq_idx);
       // aSFK: I_a + ca*Etot*I_i/(1 + cf*Etot) = (I_a + (cf*I_a + ca*I_i)*Etot)/(1 + cf*Etot)   (basepdesolver.jl:206-207)
       const double cr = lane == aSFK ? fma(cf, Iq, ca * lds(ws_s + 8 * iSFK)) : cr_fixed;
-      if constexpr (PIPE) {
-        // this step's edge nodes for the neighbours' next step: every lane has finished reading the old ones (the barrier
-        // above), and the barrier below the fixed point separates these stores from the loads at the top of the next step
-#pragma unroll
-        for (int p = 0; p < NCY / 2; ++p) {
-          if (lane != lane_b) sts2(ex_own + 512u * p, u[2 * p][K - 1], u[2 * p + 1][K - 1]);
-          sts2(ex_own + 512u * (NCY / 2 + p), u[2 * p][0], u[2 * p + 1][0]);
-        }
-      }
 
       // ---- fixed-point iterations (basepdesolver.jl:197-242); the first pass is peeled: its reciprocal is ready ----
       int it = 1;               // the host routes `maxiters = 0` to the strict kernel: at least one pass runs here
@@ -864,18 +824,11 @@ __device__ void solve_set(const KernelArgs& a, long long set, int lane, double* 
       }
       bc_total += it;
       // ---- boundary values back to the lane that owns node Nr ----
-      if constexpr (PIPE) {
-        sts(x_st, x);
-        __syncwarp();
+      if (lane < NCY) sts(ws_s + 8 * (16 + lane), x);
+      __syncwarp();
+      if (lane == lane_b) {
 #pragma unroll
-        for (int p = 0; p < NCY / 2; ++p) lds2(ex_own + 512u * p, u[2 * p][K - 1], u[2 * p + 1][K - 1]);
-      } else {
-        if (lane < NCY) sts(ws_s + 8 * (16 + lane), x);
-        __syncwarp();
-        if (lane == lane_b) {
-#pragma unroll
-          for (int q = 0; q < NCY; ++q) u[q][idx_b] = lds(ws_s + 8 * (16 + q));
-        }
+        for (int q = 0; q < NCY; ++q) u[q][idx_b] = lds(ws_s + 8 * (16 + q));
       }
       if (unconverged || nan_exit) {
         bool all_nan = (lane < ML || lane >= LE) || isnan(x);
