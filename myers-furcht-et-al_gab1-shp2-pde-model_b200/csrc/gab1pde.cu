@@ -189,9 +189,11 @@ int solve_with_gangs(const GangPick& gp, int mode, gab1::KernelArgs a, const Wor
 //                    on shards of the 10^5-draw bench ensemble: longest set / share = 1.59 gains 12 %, 0.96 / 0.85 / 0.80 gain
 //                    nothing (profiles/r2_latency_lane_probe.jsonl); round 2's first threshold of 0.5 sent 74 sets of a uniform
 //                    two-sets-per-warp batch (2368 posterior rows at dr = 0.1) to the lane and cost it 25 % (356 -> 446 ms);
-//   warps/2 < S      every set has a warp to itself: the sets within 1.6x (the duo's gain) of the longest one, as far as the
-//                    registers they take from the other kernel allow (a duo CTA displaces a four-warp CTA);
-//   S <= warps/2     every set.
+//   warps/4 < S      every set has a warp to itself and the GPU is at least half full: none.  Two warps per set execute more
+//                    instructions per step (warp B recomputes node Nr-1), which costs more than the shorter chain saves once the
+//                    schedulers are shared: 592 / 900 / 1184 posterior rows 30.7 / 31.5 / 37.8 ms one warp per set against
+//                    35.9 / 36.4 / 41.0 ms with the lane (gpurun_out/r2n_duo_probe.jsonl);
+//   S <= warps/4     every set (1 / 64 / 296 rows: 16.5 / 19.4 / 20.0 ms against 17.5 / 21.4 / 21.7 ms).
 __global__ void __launch_bounds__(1024) duo_plan_kernel(long long S, const unsigned* keys, long long warps, int nsm, int all,
                                                         unsigned* counter) {
   __shared__ unsigned long long s_part[32];
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(1024) duo_plan_kernel(long long S, const unsig
   long long cap;
   if (all) { thr = -1.0; cap = S; }
   else if (S > warps) { thr = 0.9 * (double)s_total / (double)warps; cap = nsm / 2; }
-  else if (2 * S > warps) { thr = 0.625 * (double)keys[0]; cap = (warps - S) / 4; }
+  else if (4 * S > warps) { thr = 0.0; cap = 0; }
   else { thr = -1.0; cap = S; }
   const long long lim = S < cap ? S : cap;
   unsigned local = 0;
