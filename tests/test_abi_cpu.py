@@ -68,6 +68,27 @@ def test_no_gpu_means_loud_failure_not_cpu_fallback(pkg, lib):
         pkg.host.sapdesolver(pkg.params.base_Co(), pkg.params.DIFFS_BASE, pkg.params.KVALS_BASE, tf=0.01)
 
 
+def test_certified_entry_point_validates_like_the_plain_one(pkg, lib):
+    """gab1_solve_batch_certified (gab1pde.h): same option checks, an empty batch is a no-op that clears its counters, and without a
+    GPU it fails as loudly as gab1_solve_batch — the certification is GPU work too (strict kernels), never the oracle."""
+    Co, D, k, r = pkg.params.base_Co(), pkg.params.DIFFS_BASE, pkg.params.KVALS_BASE, pkg.params.julia_range(0.2, 10.0)
+    n_res = C.c_int64(7)
+    extra = (C.c_double(0.0), None, C.byref(n_res))
+    o = pkg.abi.make_opts(dr=0.2)
+    o.abi_version = 99
+    rc, *_ = pkg.abi.call_solve(lib.gab1_solve_batch_certified, o, Co, D, k, 1e-4, r, *extra)
+    assert rc < 0 and b"abi_version" in lib.gab1_last_error() and n_res.value == 0
+    o = pkg.abi.make_opts(dr=0.2)
+    n_res.value = 7
+    rc, out, *_ = pkg.abi.call_solve(lib.gab1_solve_batch_certified, o, Co, np.zeros((0, 7)), np.zeros((0, 17)), np.zeros(0), r, *extra)
+    assert rc == 0 and out.shape[0] == 0 and n_res.value == 0
+    if lib.gab1_device_count() == 0:
+        rc, *_ = pkg.abi.call_solve(lib.gab1_solve_batch_certified, o, Co, D, k, 1e-4, r, *extra)
+        assert rc < 0 and b"no CUDA device" in lib.gab1_last_error()
+        with pytest.raises(pkg.abi.Gab1Error, match="no CUDA device"):
+            pkg.host.Frontend(pkg.abi.CudaBackend()).sapdesolver_batch(Co, D[None, :], k[None, :], tf=0.01, certify=True)
+
+
 def test_julia_range_is_correctly_rounded(pkg):
     r = pkg.params.julia_range(0.2, 10.0)
     assert len(r) == 51 and r[3] == 0.6 and r[3] != 3 * 0.2 and r[-1] == 10.0     # SURVEY.md §7 "hard parts"
