@@ -40,6 +40,9 @@ const MEMBSFK_WRAPPERS = Ref(isdefined(Main, :sapdesolver_membSFK) && !isdefined
 const ITER_CAP = Ref(2000)
 "number of GPUs a batch is sharded over inside one call; 0 = all visible"
 const N_DEVICES = Ref(0)
+"true: the GSA entry points (fbatch_*_mt, pmap_fun_*), whose reference signatures leave no room for a keyword, certify their
+batches (gab1_solve_batch_certified: ill-conditioned sets are re-solved with the strict kernels; about 2.3x the cost)"
+const CERTIFY = Ref(false)
 
 # struct gab1_opts (include/gab1pde.h) — field order and types must match exactly
 struct Opts
@@ -170,7 +173,7 @@ function variant(model_fun)
 end
 
 six(Co, Dm, km; R, dr, tf, tol, maxiters, membSFK=MEMBSFK_WRAPPERS[]) =
-    sapdesolver_batch(Co, Dm, km; R, dr, tf, tol, maxiters, membSFK, out_mode=OUT_SIX)
+    sapdesolver_batch(Co, Dm, km; R, dr, tf, tol, maxiters, membSFK, out_mode=OUT_SIX, certify=CERTIFY[])
 one(b) = (b.status[1] & ST_THROW != 0) ? throw(ArgumentError("reducing over an empty collection is not allowed")) : b.out[:, 1]
 row(v) = reshape(Float64.(v), 1, :)
 
