@@ -69,6 +69,29 @@ def test_known_diverging_row_and_nan_count(pkg, ofe, ensemble):
     assert np.isfinite(sol.PG1S).all()
 
 
+def test_run_ensemble_rows_are_the_batch_blocks_views(pkg, ofe, ensemble):
+    """host.Frontend.run_ensemble / run_ensemble_pc (the code the GPU backend runs too): every row's 21 / 22 fields are the set's
+    own blocks of the batched result, the rect solver's outputs are cut to 1 + #snapshots columns (basepdesolver_rect.jl:250-279),
+    EGFR_SHP2 sits where basepdesolver_rect.jl:282-290 puts it, and `index` is 1-based (get_param_posteriors.jl:158)."""
+    Co, abi = pkg.params.base_Co(), pkg.abi
+    sub = ensemble[72:78]
+    for name, variant in (("pdesolver", {}), ("pdesolver_rect", dict(geometry=abi.GEOM_RECT, pg1tot_form=abi.PG1TOT_CHAIN))):
+        rows = ofe.run_ensemble(name, sub, Co, Nts=10, tf=0.5, show_prog=False)
+        res = ofe.pdesolver_batch(Co, sub[:, :7], sub[:, 7:], R=10.0, dr=0.2, tf=0.5, Nts=10, tol=1e-4, maxiters=20, **variant)
+        keep = np.flatnonzero((res.status & abi.ST_NAN) == 0)
+        assert [x.index for x in rows] == (keep + 1).tolist()
+        for x, j in zip(rows, keep):
+            nc = int(res.n_saved[j]) if name == "pdesolver_rect" else 11
+            assert type(x.sol).__name__ == ("Sol22" if name == "pdesolver_rect" else "Sol21")
+            for n in abi.MATRIX_NAMES:
+                np.testing.assert_array_equal(getattr(x.sol, n), res.matrix(n)[j][:, :nc])
+            for n in abi.VECTOR_NAMES[:9] + (("EGFR_SHP2",) if name == "pdesolver_rect" else ()):
+                np.testing.assert_array_equal(getattr(x.sol, n), res.vector(n)[j][:nc])
+            np.testing.assert_array_equal(x.t_sol, res.vector("t_out")[j][:nc])
+    rows = ofe.run_ensemble_pc("pulsechase_solver", sub[:3], Co, t_prechase=0.2, t_chase=0.1, Nts=6)
+    assert [x.index for x in rows] == [1, 2, 3] and type(rows[0].sol).__name__ == "Sol22" and rows[0].sol.aSFK.shape == (51, 7)
+
+
 def test_oracle_kat(pkg, ofe, ensemble):
     """Known-answer vectors written by tests/golden/make_fixtures.py: guards the oracle's arithmetic against drift."""
     from pathlib import Path
